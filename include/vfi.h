@@ -1,0 +1,181 @@
+/*
+ * vfi.h — C ABI of the B200-native VeritasFi retrieval hot path.
+ *
+ * This is the drop-in boundary. Every entry point replaces one call the
+ * reference makes into an un-vendored CPU library; citations are relative to /root/reference/.
+ *
+ *   vfi_index_*      replaces faiss.IndexFlatIP(d) / .add / .search        src/utils/faissRetriever.py:18,24,37
+ *   vfi_normalize_l2 replaces faiss.normalize_L2(x)                         src/utils/faissRetriever.py:22,35
+ *   vfi_bm25_*       replaces bm25s.BM25.load(...) / .retrieve(tokens, k)   src/utils/bm25Retriever.py:46,75-79
+ *   vfi_fuse_union   replaces the shared seen_ids ordered de-dup union      src/utils/ensembleRetriever.py:58,72-74,148-150,194-196
+ *   vfi_fuse_rrf     reciprocal-rank fusion (north_star; not in the reference, SURVEY.md finding 4)
+ *   vfi_merge_topk   global top-k after the all-gather of per-shard results (no reference counterpart;
+ *                    the reference only replicates workers, experiments/retriever/step3_mul.py:405-446)
+ *   vfi_cosine_topk  replaces cosine_similarity + argsort top-k             experiments/retriever/step3_mul.py:255-289,
+ *                                                                           experiments/retriever/continuous_retrieval.py:154-167
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types. `mem` says where caller buffers live.
+ *   - the library never returns pointers into its own memory; the caller owns every output buffer.
+ *   - no function throws; each returns a vfi_status and vfi_last_error() holds a thread-local message.
+ *   - ids are row positions (the reference's row-id space, ensembleRetriever.py:45-48) plus the
+ *     index's id offset (used by corpus shards to emit global ids).
+ *   - result order is the total order (score descending, id ascending); rows short of k are
+ *     padded with id -1 / score -FLT_MAX like faiss.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *   - there is NO CPU implementation behind this ABI: without a CUDA device every compute entry
+ *     fails with VFI_ERR_NO_DEVICE.
+ */
+#ifndef VFI_H_
+#define VFI_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFI_ABI_VERSION 1
+
+typedef enum vfi_status {
+  VFI_OK = 0,
+  VFI_ERR_INVALID = 1,     /* bad argument (dimension mismatch, k <= 0, null pointer ...) */
+  VFI_ERR_CUDA = 2,        /* a CUDA runtime/driver call failed; message has the detail */
+  VFI_ERR_NOMEM = 3,       /* device or host allocation failed */
+  VFI_ERR_UNSUPPORTED = 4, /* outside the supported envelope (e.g. k > VFI_MAX_K) */
+  VFI_ERR_NO_DEVICE = 5,   /* no CUDA device / not an sm_100 device */
+  VFI_ERR_INTERNAL = 6
+} vfi_status;
+
+/* where a caller buffer lives */
+enum { VFI_MEM_HOST = 0, VFI_MEM_DEVICE = 1 };
+
+/* how corpus rows are stored (and therefore what "the corpus" is for parity purposes)
+ *   VFI_STORE_BF16: rows and queries are rounded to bf16 (round-to-nearest-even) on entry; the
+ *                   canonical score is the exact dot product of those bf16 values.
+ *   VFI_STORE_F32 : rows and queries keep their fp32 values (faiss.IndexFlatIP semantics); the
+ *                   tensor-core pass runs on a 3-term bf16 split, the exact pass on the fp32 rows. */
+enum { VFI_STORE_BF16 = 0, VFI_STORE_F32 = 1 };
+
+#define VFI_MAX_K 2048
+
+typedef struct vfi_index vfi_index_t;
+typedef struct vfi_bm25 vfi_bm25_t;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int vfi_abi_version(void);
+const char* vfi_last_error(void);
+/* number of usable CUDA devices (0 when there is none); never fails */
+int vfi_device_count(void);
+/* kernels launched by this library since load (all threads); for bench.py's gpu_launches */
+int64_t vfi_launch_count(void);
+
+/* ---- dense flat inner-product index (faiss.IndexFlatIP) ---------------------------------- */
+int vfi_index_create(int d, int store_dtype, int device, vfi_index_t** out);
+int vfi_index_destroy(vfi_index_t* idx);
+/* reserve device capacity for n rows in total (optional; add() grows geometrically otherwise) */
+int vfi_index_reserve(vfi_index_t* idx, int64_t n);
+/* append n fp32 rows [n,d] row-major; copies (the caller's array may be freed afterwards) */
+int vfi_index_add(vfi_index_t* idx, const float* x, int64_t n, int mem, void* stream);
+/* append n bf16 rows (raw 16-bit patterns); only for VFI_STORE_BF16 indexes */
+int vfi_index_add_bf16(vfi_index_t* idx, const uint16_t* x, int64_t n, int mem, void* stream);
+int64_t vfi_index_ntotal(const vfi_index_t* idx);
+int vfi_index_dim(const vfi_index_t* idx);
+/* ids reported by search = row position + offset (corpus shards report global ids) */
+int vfi_index_set_id_offset(vfi_index_t* idx, int64_t offset);
+/* copy row i (as fp32, the stored value) to out[d] */
+int vfi_index_reconstruct(vfi_index_t* idx, int64_t i, float* out, int mem);
+/* exact top-k of q·xᵀ. q: fp32 [nq,d]; out_scores fp32 [nq,k]; out_ids int64 [nq,k].
+ * Blocks until the results are in the caller's buffers when mem == VFI_MEM_HOST; with
+ * VFI_MEM_DEVICE the call returns after the device work is enqueued and verified. */
+int vfi_index_search(vfi_index_t* idx, const float* q, int64_t nq, int k, float* out_scores,
+                     int64_t* out_ids, int mem, void* stream);
+
+/* tuning / introspection ------------------------------------------------------------------ */
+enum {
+  VFI_OPT_OVERFETCH = 1,     /* candidates kept per query by the tensor-core pass (0 = auto) */
+  VFI_OPT_FORCE_PATH = 2,    /* 0 auto, 1 exhaustive exact, 2 fused tcgen05, 3 streaming GEMV */
+  VFI_OPT_PROFILE = 3,       /* 1: bracket the dominant kernel with CUDA events */
+  VFI_OPT_TAU_HINT = 4,      /* 1: estimate a per-query admission threshold from a row sample */
+  VFI_OPT_NUM_CTAS = 5       /* 0 = one CTA per SM */
+};
+int vfi_index_set_option(vfi_index_t* idx, int opt, int64_t value);
+
+typedef struct vfi_search_stats {
+  int64_t searches;            /* search calls */
+  int64_t queries;             /* queries processed */
+  int64_t retried_queries;     /* queries whose certificate failed and were re-run exhaustively */
+  int64_t fused_launches;      /* launches of the tcgen05 kernel */
+  double fused_ms_total;       /* summed device time of those launches (VFI_OPT_PROFILE=1) */
+  int64_t fused_ms_samples;    /* launches that contributed to fused_ms_total */
+  int last_path;               /* path taken by the last search (VFI_OPT_FORCE_PATH values) */
+  int last_overfetch;          /* k' used by the last search */
+  float last_eps;              /* largest certificate epsilon of the last search */
+  float max_abs_err;           /* max |tensor-core score - exact score| over rescored candidates */
+} vfi_search_stats;
+int vfi_index_get_stats(vfi_index_t* idx, vfi_search_stats* out, int reset);
+
+/* debug/test hook: raw tensor-core scores S[nq, n] of the first n rows (device or host buffer) */
+int vfi_index_debug_scores(vfi_index_t* idx, const float* q, int64_t nq, float* out, int mem,
+                           void* stream);
+
+/* in-place row-wise L2 normalisation in fp32, zero rows untouched (faiss.normalize_L2) */
+int vfi_normalize_l2(float* x, int64_t n, int d, int mem, int device, void* stream);
+
+/* exact cosine top-k between two small fp32 matrices (the experiments' select_top_chunks):
+ * tie order "higher index first" as produced by np.argsort(sim)[-k:][::-1] */
+int vfi_cosine_topk(const float* e, int64_t n_e, const float* c, int64_t n_c, int d, int k,
+                    float* out_scores, int64_t* out_ids, int mem, int device, void* stream);
+
+/* ---- multi-GPU merge --------------------------------------------------------------------- */
+/* scores fp32 [g, nq, k_in], ids int64 [g, nq, k_in] (id -1 = padding) -> top k_out per query */
+int vfi_merge_topk(const float* scores, const int64_t* ids, int g, int64_t nq, int k_in,
+                   int k_out, float* out_scores, int64_t* out_ids, int mem, int device,
+                   void* stream);
+
+/* ---- BM25 over token-major postings (bm25s CSC arrays) ----------------------------------- */
+/* indptr int64 [n_vocab+1], indices int32 [nnz] (doc ids ascending per token), data fp32 [nnz]
+ * (precomputed impacts). doc ids are local to this shard in [0, n_docs); reported ids add
+ * id_offset. Host pointers; the arrays are copied to the device. */
+int vfi_bm25_create(const int64_t* indptr, const int32_t* indices, const float* data,
+                    int64_t n_vocab, int64_t n_docs, int64_t id_offset, int device,
+                    vfi_bm25_t** out);
+int vfi_bm25_destroy(vfi_bm25_t* b);
+int64_t vfi_bm25_ndocs(const vfi_bm25_t* b);
+/* q_tokens int32 [q_indptr[nq]] token ids in query order (unknown tokens already dropped,
+ * repeats kept), q_indptr int64 [nq+1]. Scores accumulate in fp32 in query-token order. */
+int vfi_bm25_search(vfi_bm25_t* b, const int32_t* q_tokens, const int64_t* q_indptr, int64_t nq,
+                    int k, float* out_scores, int64_t* out_ids, int mem, void* stream);
+/* all n_docs scores of one query (host/device fp32 [n_docs]); serves retrieve(k = N) */
+int vfi_bm25_score_all(vfi_bm25_t* b, const int32_t* q_tokens, int64_t n_tokens, float* out,
+                       int mem, void* stream);
+/* every doc ranked: out_ids int64 [n_docs], out_scores fp32 [n_docs] in (score desc, id asc)
+ * order — bm25s retrieve(k = N) as called at ensembleRetriever.py:189. Host outputs. */
+int vfi_bm25_rank_all(vfi_bm25_t* b, const int32_t* q_tokens, int64_t n_tokens, float* out_scores,
+                      int64_t* out_ids, void* stream);
+typedef struct vfi_bm25_stats {
+  int64_t launches;
+  double score_ms_total;   /* device time of the scoring kernel (profile on) */
+  int64_t score_ms_samples;
+  int64_t postings_bytes;  /* algorithmic bytes of the last search: sum over query tokens df*8 */
+} vfi_bm25_stats;
+int vfi_bm25_set_profile(vfi_bm25_t* b, int on);
+int vfi_bm25_get_stats(vfi_bm25_t* b, vfi_bm25_stats* out, int reset);
+
+/* ---- rank fusion -------------------------------------------------------------------------- */
+/* ids int64 [nq, n_paths, depth] ranked lists (-1 = padding, rank = position+1).
+ * fused(d) = sum over paths p=0.. of 1/(k_rrf + rank_p(d)) in fp32, in path order.
+ * out: top k by (fused desc, id asc). */
+int vfi_fuse_rrf(const int64_t* ids, int64_t nq, int n_paths, int depth, float k_rrf, int k,
+                 float* out_scores, int64_t* out_ids, int mem, int device, void* stream);
+/* priority-ordered de-duplicated union (path 0 first, rank order inside a path; first
+ * occurrence wins). out_ids/out_scores/out_path [nq, n_paths*depth] padded with -1;
+ * out_count int32 [nq]. */
+int vfi_fuse_union(const int64_t* ids, const float* scores, int64_t nq, int n_paths, int depth,
+                   int64_t* out_ids, float* out_scores, int32_t* out_path, int32_t* out_count,
+                   int mem, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFI_H_ */

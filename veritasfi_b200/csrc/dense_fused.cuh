@@ -1,0 +1,241 @@
+// dense_fused.cuh — K1: S = Q·Dᵀ on the 5th-gen tensor cores with the top-k' selection fused into
+// the TMEM epilogue, so the score matrix never reaches HBM.
+//
+// Replaces the hot loop of faiss.IndexFlatIP.search (sgemm + heap) called at
+// /root/reference/src/utils/faissRetriever.py:37.
+//
+// Shape of the computation
+//   M = queries (128 per CTA, one TMEM lane = one query), N = corpus rows (256 per MMA, one TMEM
+//   column = one row), K = embedding dimension streamed in 64-element (128-byte) blocks.
+//   A = Q tile [128 x 64] bf16, B = D tile [256 x 64] bf16, both K-major, 128B-swizzled, staged by
+//   TMA through a 4-deep mbarrier ring.  D accumulates in TMEM (fp32, 2 x 256 columns, double
+//   buffered) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Work decomposition
+//   CTA c handles query tile m = c % n_mtiles for the corpus tiles t = g, g+G, g+2G .. of its
+//   group g = c / n_mtiles.  The n_mtiles CTAs of a group stream the same corpus tile at the same
+//   time, so each corpus tile leaves HBM once and is shared through L2.
+//
+// Selection (MODE_TOPK)
+//   Each epilogue thread owns one query for the whole kernel: its admission threshold lives in
+//   registers, admitted (score,id) keys are appended to a per-(group,query) buffer in global
+//   memory (L2 resident, written rarely) and when a buffer fills the warp compacts it to the
+//   exact k' best keys (warp_select_compact) and raises the threshold.  Only rows that can still
+//   enter the top-k' ever leave the SM.
+#pragma once
+#include "ptx.cuh"
+#include "topk_common.cuh"
+
+namespace vfi {
+
+constexpr int kBM = 128;
+constexpr int kBN = 256;
+constexpr int kBK = 64;
+constexpr int kStages = 4;
+constexpr int kABytes = kBM * kBK * 2;   // 16 KB
+constexpr int kBBytes = kBN * kBK * 2;   // 32 KB
+constexpr int kDenseThreads = 256;       // warps 0-3: TMA / MMA / TMEM-alloc / spare, 4-7: epilogue
+constexpr int kTmemCols = 512;
+constexpr int kDenseSmemBytes =
+    1024 /*align slack*/ + kStages * (kABytes + kBBytes) + 256 /*barriers*/ + 4 * 256 * 4 /*hist*/;
+
+enum { MODE_TOPK = 0, MODE_STORE = 1 };
+
+struct DenseParams {
+  int nq;                 // queries in this launch
+  int nq_pad;             // n_mtiles * 128
+  int n_rows;             // corpus rows
+  int n_kblocks;          // K' / 64
+  int n_mtiles;
+  int n_groups;
+  int n_tiles;            // ceil(n_rows / 256)
+  int keep;               // k'
+  int cap;                // keys per (group, query) buffer; cap >= keep + 64
+  uint64_t* cand;         // [n_groups][nq_pad][cap]
+  uint32_t* cand_count;   // [n_groups][nq_pad]
+  const float* tau_init;  // [nq] admission hints (rows with score <= hint are ignored) or nullptr
+  float* scores_out;      // MODE_STORE: [nq_pad][ld_scores]
+  int64_t ld_scores;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kDenseThreads, 1)
+dense_fused_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                   const __grid_constant__ CUtensorMap tmap_d, const DenseParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kStages * kBBytes);
+  uint64_t* full_bar = bars;                   // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;        // [kStages]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * kStages;    // [2]        MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]     epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 256);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_q);
+    ptx::prefetch_tmap(&tmap_d);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull_bar[i], 1);
+      ptx::mbar_init(&tempty_bar[i], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tile = static_cast<int>(blockIdx.x) % p.n_mtiles;
+  const int group = static_cast<int>(blockIdx.x) / p.n_mtiles;
+  const bool active = group < p.n_groups;
+  const int nkb = p.n_kblocks;
+
+  if (active && warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    uint32_t stage = 0, phase = 0;
+    const uint64_t d_hint = (p.n_mtiles > 1) ? ptx::kEvictNormal : ptx::kEvictFirst;
+    for (int t = group; t < p.n_tiles; t += p.n_groups) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        ptx::mbar_expect_tx(&full_bar[stage], kABytes + kBBytes);
+        ptx::tma_load_2d(sA + stage * kABytes, &tmap_q, &full_bar[stage], kb * kBK,
+                         m_tile * kBM, ptx::kEvictLast);
+        ptx::tma_load_2d(sB + stage * kBBytes, &tmap_d, &full_bar[stage], kb * kBK, t * kBN,
+                         d_hint);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (active && warp == 1 && lane == 0) {
+    // ===================== MMA issuer (one thread) =====================
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBM, kBN);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int t = group; t < p.n_tiles; t += p.n_groups) {
+      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kBN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t a_addr = ptx::smem_u32(sA + stage * kABytes);
+        const uint32_t b_addr = ptx::smem_u32(sB + stage * kBBytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          ptx::umma_bf16_ss(d_tmem, ptx::umma_desc_k128(a_addr + k * 32),
+                            ptx::umma_desc_k128(b_addr + k * 32), idesc,
+                            (kb | k) != 0 ? 1u : 0u);
+        }
+        ptx::tc_commit(&empty_bar[stage]);               // frees the smem stage when MMAs retire
+        if (kb == nkb - 1) ptx::tc_commit(&tfull_bar[acc]);  // accumulator complete
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (active && warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> threshold filter =====================
+    const uint32_t wq = warp - 4;                 // TMEM lane quadrant of this warp
+    const int qi = m_tile * kBM + wq * 32 + lane;  // the query this thread owns
+    const bool valid_q = qi < p.nq;
+    uint32_t* my_hist = hist + wq * 256;
+
+    uint64_t* buf = nullptr;
+    uint32_t count = 0;
+    uint64_t tau_key = kKeyNone;
+    float tau_f = -INFINITY;
+    if (MODE == MODE_TOPK) {
+      buf = p.cand + (static_cast<size_t>(group) * p.nq_pad + qi) * p.cap;
+      if (valid_q && p.tau_init != nullptr) {
+        tau_f = p.tau_init[qi];
+        tau_key = make_key(tau_f, 0u);   // admits score > hint only
+      }
+    }
+    uint32_t acc = 0, acc_phase = 0;
+    for (int t = group; t < p.n_tiles; t += p.n_groups) {
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t row0 = static_cast<uint32_t>(t) * kBN;
+      const uint32_t taddr = tmem_base + ((wq * 32u) << 16) + acc * kBN;
+#pragma unroll 1
+      for (int c = 0; c < kBN / 32; ++c) {
+        float v[32];
+        ptx::tmem_ld_32x32(taddr + c * 32, v);
+        ptx::tmem_ld_wait();
+        if (MODE == MODE_STORE) {
+          if (valid_q) {
+            float4* dst = reinterpret_cast<float4*>(p.scores_out + static_cast<size_t>(qi) * p.ld_scores +
+                                                    row0 + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        } else {
+          float mx = v[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+          if (valid_q && mx >= tau_f) {
+            const uint32_t id0 = row0 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (v[j] >= tau_f && id0 + j < static_cast<uint32_t>(p.n_rows)) {
+                const uint64_t key = make_key(v[j], id0 + j);
+                if (key > tau_key) buf[count++] = key;
+              }
+            }
+          }
+          // a buffer that cannot take another 32 keys is compacted now (warp-cooperative)
+          uint32_t need = __ballot_sync(0xFFFFFFFFu, count + 32 > static_cast<uint32_t>(p.cap));
+          while (need) {
+            const uint32_t src = __ffs(need) - 1;
+            need &= need - 1;
+            uint64_t* sbuf = reinterpret_cast<uint64_t*>(
+                __shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(buf), src));
+            const uint32_t sn = __shfl_sync(0xFFFFFFFFu, count, src);
+            __syncwarp();
+            const uint64_t kth = warp_select_compact(sbuf, sn, p.keep, my_hist, lane);
+            if (lane == src) {
+              count = p.keep;
+              tau_key = kth;
+              tau_f = key_score(kth);
+            }
+            __syncwarp();
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (MODE == MODE_TOPK) {
+      p.cand_count[static_cast<size_t>(group) * p.nq_pad + qi] = valid_q ? count : 0u;
+    }
+  }
+
+  // teardown
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace vfi

@@ -1,0 +1,102 @@
+// select.cuh — block-level exact top-k over 64-bit keys (see topk_common.cuh for the order).
+// Used by: candidate reduction after the fused GEMM (K1c), the final ordering after exact
+// rescoring (K2), the multi-GPU merge (K3), the BM25 reduction (K4) and rank fusion (K5).
+#pragma once
+#include "topk_common.cuh"
+
+namespace vfi {
+
+constexpr uint32_t kSortCap = 4096;  // keys sortable in shared memory by one CTA (32 KB)
+
+struct SelectSmem {
+  uint64_t keys[kSortCap];
+  uint32_t hist[256];
+  uint32_t ctr;
+  uint32_t digit, before, cnt;
+};
+
+__device__ __forceinline__ uint32_t next_pow2(uint32_t x) {
+  uint32_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+// warp 0: find the bin holding the `remaining`-th largest key given the 256-bin histogram
+__device__ __forceinline__ void hist_find_bin(const uint32_t* hist, uint32_t remaining,
+                                              uint32_t lane, uint32_t* o_digit,
+                                              uint32_t* o_before, uint32_t* o_cnt) {
+  uint32_t c[8];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i] = hist[lane * 8 + i]; mine += c[i]; }
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_down_sync(0xFFFFFFFFu, incl, o);
+    if (lane + o < 32) incl += t;
+  }
+  const uint32_t above = incl - mine;
+  if (above < remaining && remaining <= above + mine) {
+    uint32_t run = above;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      if (run < remaining && remaining <= run + c[i]) {
+        *o_digit = lane * 8 + i;
+        *o_before = run;
+        *o_cnt = c[i];
+      }
+      run += c[i];
+    }
+  }
+}
+
+// Src: struct with   template<class F> __device__ void for_each(F f) const
+// calling f(key) for the keys assigned to this thread (each key visited by exactly one thread).
+// Leaves the min(total,k) best keys sorted descending in sm->keys[0..); returns that count.
+// Keys must be distinct and != 0.  k <= kSortCap.  All threads of the block must call.
+template <class Src>
+__device__ uint32_t block_topk(const Src& src, uint32_t total, uint32_t k, SelectSmem* sm) {
+  const uint32_t tid = threadIdx.x;
+  uint64_t thresh = 0;  // keep keys >= thresh
+  uint32_t n_keep = total;
+  if (total > kSortCap) {
+    // MSD radix walk for the exact k-th largest key
+    uint64_t prefix = 0;
+    uint32_t remaining = k;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      if (tid < 256) sm->hist[tid] = 0;
+      __syncthreads();
+      const uint64_t himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
+      src.for_each([&](uint64_t key) {
+        if ((key & himask) == prefix) atomicAdd(&sm->hist[(key >> shift) & 0xFF], 1u);
+      });
+      __syncthreads();
+      if (tid < 32) hist_find_bin(sm->hist, remaining, tid, &sm->digit, &sm->before, &sm->cnt);
+      __syncthreads();
+      prefix |= static_cast<uint64_t>(sm->digit) << shift;
+      remaining -= sm->before;
+      const bool stop = (sm->cnt == remaining) || shift == 0;
+      __syncthreads();
+      if (stop) break;
+    }
+    thresh = prefix;
+    n_keep = k;
+  }
+  if (tid == 0) sm->ctr = 0;
+  __syncthreads();
+  src.for_each([&](uint64_t key) {
+    if (key >= thresh && key != 0ull) {
+      uint32_t pos = atomicAdd(&sm->ctr, 1u);
+      if (pos < kSortCap) sm->keys[pos] = key;
+    }
+  });
+  __syncthreads();
+  uint32_t n = min(sm->ctr, kSortCap);
+  (void)n_keep;
+  const uint32_t np = max(next_pow2(n), 2u);
+  for (uint32_t i = n + tid; i < np; i += blockDim.x) sm->keys[i] = 0ull;
+  block_bitonic_desc(sm->keys, np);
+  return min(n, k);
+}
+
+}  // namespace vfi

@@ -1,0 +1,1167 @@
+// vfi_api.cu — the C ABI declared in include/vfi.h: host orchestration of the CUDA kernels.
+// One translation unit builds libvfi.so:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC vfi_api.cu
+// There is no CPU implementation here; every compute entry needs an sm_100 device.
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/vfi.h"
+#include "dense_fused.cuh"
+#include "dense_support.cuh"
+#include "sparse_fuse.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define VFI_CUDA(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      return fail(e__ == cudaErrorMemoryAllocation ? VFI_ERR_NOMEM : VFI_ERR_CUDA,           \
+                  std::string(#expr) + ": " + cudaGetErrorString(e__));                      \
+    }                                                                                        \
+  } while (0)
+#define VFI_TRY(expr)              \
+  do {                             \
+    int s__ = (expr);              \
+    if (s__ != VFI_OK) return s__; \
+  } while (0)
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+// grow-only device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return VFI_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    size_t want = std::max(need, static_cast<size_t>(256));
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(VFI_ERR_NOMEM, std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+    }
+    bytes = want;
+    return VFI_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    ok = (cudaSetDevice(dev) == cudaSuccess);
+    if (!ok) cudaGetLastError();
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
+// bf16 row-major [rows][cols] with 128B swizzle, box = [box_rows][64]
+int make_tmap(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t pitch_elems, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return fail(VFI_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch_elems) * 2};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VFI_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+  return VFI_OK;
+}
+
+int device_props(int device, cudaDeviceProp* prop) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(VFI_ERR_NO_DEVICE, "no CUDA device: this library has no CPU implementation");
+  }
+  if (device < 0 || device >= n) return fail(VFI_ERR_INVALID, "device index out of range");
+  VFI_CUDA(cudaGetDeviceProperties(prop, device));
+  if (prop->major != 10)
+    return fail(VFI_ERR_NO_DEVICE, std::string("device '") + prop->name + "' is not sm_100 (kernels are built for sm_100a only)");
+  return VFI_OK;
+}
+
+constexpr int kMaxQueriesPerLaunch = 1024;
+constexpr int kExhaustiveRows = 4096;   // shards this small skip the tensor-core pass
+constexpr int kFusedMaxKeep = 1024;
+constexpr int kGemvMaxKeep = 512;
+
+}  // namespace
+
+// =============================================================================================
+struct vfi_index {
+  int d = 0, dp = 0, store = VFI_STORE_BF16, device = 0;
+  int64_t kp = 0;          // gemm operand row length (dp or 3*dp)
+  int64_t n = 0, cap_rows = 0;
+  int64_t id_offset = 0;
+  int num_sms = 148;
+  uint16_t* g = nullptr;   // [cap_rows][kp] bf16 gemm operand rows
+  float* master = nullptr; // [cap_rows][dp] fp32 rows (F32 store only)
+  uint32_t* xnorm_bits = nullptr;
+  // options
+  int64_t opt_overfetch = 0, opt_force_path = 0, opt_profile = 0, opt_tau_hint = 0, opt_num_ctas = 0;
+  // workspace
+  DevBuf w_qin, w_qcanon, w_qg, w_eps, w_cand, w_cand_count, w_keys, w_keys_n, w_bound, w_keys2, w_flag,
+      w_out_scores, w_out_ids, w_stage, w_dbg, w_sel, w_tau;
+  int* h_flag = nullptr;   // pinned: [0] = n_flagged, [1..] = flagged query ids
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  vfi_search_stats stats{};
+  uint32_t* d_max_err = nullptr;
+  std::mutex mu;
+};
+
+extern "C" {
+
+int vfi_abi_version(void) { return VFI_ABI_VERSION; }
+const char* vfi_last_error(void) { return g_err.c_str(); }
+int vfi_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+int64_t vfi_launch_count(void) { return g_launches.load(); }
+
+int vfi_index_create(int d, int store_dtype, int device, vfi_index_t** out) {
+  if (!out) return fail(VFI_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (d <= 0 || d > 8192) return fail(VFI_ERR_INVALID, "dimension must be in [1, 8192]");
+  if (store_dtype != VFI_STORE_BF16 && store_dtype != VFI_STORE_F32) return fail(VFI_ERR_INVALID, "unknown store_dtype");
+  cudaDeviceProp prop;
+  VFI_TRY(device_props(device, &prop));
+  DeviceGuard guard(device);
+  vfi_index* idx = new vfi_index();
+  idx->d = d;
+  idx->dp = static_cast<int>(round_up(d, 64));
+  idx->store = store_dtype;
+  idx->kp = (store_dtype == VFI_STORE_F32) ? 3 * static_cast<int64_t>(idx->dp) : idx->dp;
+  idx->device = device;
+  idx->num_sms = prop.multiProcessorCount;
+  auto bail = [&](int code) {
+    vfi_index_destroy(idx);
+    return code;
+  };
+  if (cudaMalloc(&idx->xnorm_bits, 8) != cudaSuccess) return bail(fail(VFI_ERR_NOMEM, "cudaMalloc failed"));
+  cudaMemset(idx->xnorm_bits, 0, 8);
+  idx->d_max_err = idx->xnorm_bits + 1;
+  if (cudaMallocHost(&idx->h_flag, sizeof(int) * (kMaxQueriesPerLaunch + 1)) != cudaSuccess)
+    return bail(fail(VFI_ERR_NOMEM, "cudaMallocHost failed"));
+  cudaEventCreate(&idx->ev0);
+  cudaEventCreate(&idx->ev1);
+  cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kDenseSmemBytes);
+  cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kDenseSmemBytes);
+  cudaFuncSetAttribute(vfi::gemv_topk_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(vfi::gemv_topk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return bail(fail(VFI_ERR_CUDA, std::string("kernel attribute setup: ") + cudaGetErrorString(e)));
+  *out = idx;
+  return VFI_OK;
+}
+
+int vfi_index_destroy(vfi_index_t* idx) {
+  if (!idx) return VFI_OK;
+  DeviceGuard guard(idx->device);
+  cudaDeviceSynchronize();
+  if (idx->g) cudaFree(idx->g);
+  if (idx->master) cudaFree(idx->master);
+  if (idx->xnorm_bits) cudaFree(idx->xnorm_bits);
+  if (idx->h_flag) cudaFreeHost(idx->h_flag);
+  if (idx->ev0) cudaEventDestroy(idx->ev0);
+  if (idx->ev1) cudaEventDestroy(idx->ev1);
+  for (DevBuf* b : {&idx->w_qin, &idx->w_qcanon, &idx->w_qg, &idx->w_eps, &idx->w_cand, &idx->w_cand_count, &idx->w_keys,
+                    &idx->w_keys_n, &idx->w_bound, &idx->w_keys2, &idx->w_flag, &idx->w_out_scores, &idx->w_out_ids,
+                    &idx->w_stage, &idx->w_dbg, &idx->w_sel, &idx->w_tau})
+    b->release();
+  cudaGetLastError();
+  delete idx;
+  return VFI_OK;
+}
+
+}  // extern "C"
+
+static int grow_rows(vfi_index* idx, int64_t need_rows, cudaStream_t st) {
+  if (need_rows <= idx->cap_rows) return VFI_OK;
+  int64_t new_cap = std::max<int64_t>(need_rows, idx->cap_rows + idx->cap_rows / 2);
+  new_cap = std::max<int64_t>(new_cap, 1024);
+  uint16_t* ng = nullptr;
+  float* nm = nullptr;
+  cudaError_t e = cudaMalloc(&ng, static_cast<size_t>(new_cap) * idx->kp * 2);
+  if (e != cudaSuccess) return fail(VFI_ERR_NOMEM, std::string("cudaMalloc corpus: ") + cudaGetErrorString(e));
+  if (idx->store == VFI_STORE_F32) {
+    e = cudaMalloc(&nm, static_cast<size_t>(new_cap) * idx->dp * 4);
+    if (e != cudaSuccess) {
+      cudaFree(ng);
+      return fail(VFI_ERR_NOMEM, std::string("cudaMalloc corpus master: ") + cudaGetErrorString(e));
+    }
+  }
+  if (idx->n > 0) {
+    VFI_CUDA(cudaMemcpyAsync(ng, idx->g, static_cast<size_t>(idx->n) * idx->kp * 2, cudaMemcpyDeviceToDevice, st));
+    if (nm) VFI_CUDA(cudaMemcpyAsync(nm, idx->master, static_cast<size_t>(idx->n) * idx->dp * 4, cudaMemcpyDeviceToDevice, st));
+    VFI_CUDA(cudaStreamSynchronize(st));
+  }
+  if (idx->g) cudaFree(idx->g);
+  if (idx->master) cudaFree(idx->master);
+  idx->g = ng;
+  idx->master = nm;
+  idx->cap_rows = new_cap;
+  return VFI_OK;
+}
+
+extern "C" int vfi_index_reserve(vfi_index_t* idx, int64_t n) {
+  if (!idx) return fail(VFI_ERR_INVALID, "index is null");
+  std::lock_guard<std::mutex> lock(idx->mu);
+  DeviceGuard guard(idx->device);
+  return grow_rows(idx, n, nullptr);
+}
+
+template <typename InT>
+static int add_rows(vfi_index* idx, const InT* x, int64_t n, int mem, cudaStream_t st) {
+  if (n == 0) return VFI_OK;
+  if (idx->n + n >= 0x7FFFFF00ll) return fail(VFI_ERR_UNSUPPORTED, "a shard holds at most 2^31-256 rows");
+  VFI_TRY(grow_rows(idx, idx->n + n, st));
+  const int64_t chunk = std::max<int64_t>(1, (static_cast<int64_t>(256) << 20) / (static_cast<int64_t>(idx->d) * sizeof(InT)));
+  for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+    const int64_t rows = std::min(chunk, n - r0);
+    const InT* src = x + r0 * idx->d;
+    if (mem == VFI_MEM_HOST) {
+      VFI_TRY(idx->w_stage.ensure(static_cast<size_t>(rows) * idx->d * sizeof(InT)));
+      VFI_CUDA(cudaMemcpyAsync(idx->w_stage.p, src, static_cast<size_t>(rows) * idx->d * sizeof(InT), cudaMemcpyHostToDevice, st));
+      src = idx->w_stage.as<InT>();
+    }
+    const int threads = 256;
+    const int64_t blocks = ceil_div(rows * 32, threads);
+    uint16_t* gdst = idx->g + (idx->n + r0) * idx->kp;
+    if (idx->store == VFI_STORE_F32) {
+      vfi::prep_rows_kernel<true, InT><<<static_cast<unsigned>(blocks), threads, 0, st>>>(
+          src, rows, idx->d, idx->dp, gdst, idx->kp, idx->master + (idx->n + r0) * idx->dp, idx->xnorm_bits);
+    } else {
+      vfi::prep_rows_kernel<false, InT><<<static_cast<unsigned>(blocks), threads, 0, st>>>(
+          src, rows, idx->d, idx->dp, gdst, idx->kp, nullptr, idx->xnorm_bits);
+    }
+    LAUNCHED();
+    VFI_CUDA(cudaGetLastError());
+    if (mem == VFI_MEM_HOST) VFI_CUDA(cudaStreamSynchronize(st));  // staging buffer is reused
+  }
+  VFI_CUDA(cudaStreamSynchronize(st));
+  idx->n += n;
+  return VFI_OK;
+}
+
+extern "C" {
+
+int vfi_index_add(vfi_index_t* idx, const float* x, int64_t n, int mem, void* stream) {
+  if (!idx || (!x && n > 0) || n < 0) return fail(VFI_ERR_INVALID, "bad argument to vfi_index_add");
+  std::lock_guard<std::mutex> lock(idx->mu);
+  DeviceGuard guard(idx->device);
+  return add_rows<float>(idx, x, n, mem, static_cast<cudaStream_t>(stream));
+}
+
+int vfi_index_add_bf16(vfi_index_t* idx, const uint16_t* x, int64_t n, int mem, void* stream) {
+  if (!idx || (!x && n > 0) || n < 0) return fail(VFI_ERR_INVALID, "bad argument to vfi_index_add_bf16");
+  if (idx->store != VFI_STORE_BF16) return fail(VFI_ERR_INVALID, "add_bf16 needs a VFI_STORE_BF16 index");
+  std::lock_guard<std::mutex> lock(idx->mu);
+  DeviceGuard guard(idx->device);
+  return add_rows<uint16_t>(idx, x, n, mem, static_cast<cudaStream_t>(stream));
+}
+
+int64_t vfi_index_ntotal(const vfi_index_t* idx) { return idx ? idx->n : 0; }
+int vfi_index_dim(const vfi_index_t* idx) { return idx ? idx->d : 0; }
+
+int vfi_index_set_id_offset(vfi_index_t* idx, int64_t offset) {
+  if (!idx || offset < 0) return fail(VFI_ERR_INVALID, "bad id offset");
+  idx->id_offset = offset;
+  return VFI_OK;
+}
+
+int vfi_index_set_option(vfi_index_t* idx, int opt, int64_t value) {
+  if (!idx) return fail(VFI_ERR_INVALID, "index is null");
+  std::lock_guard<std::mutex> lock(idx->mu);
+  switch (opt) {
+    case VFI_OPT_OVERFETCH: idx->opt_overfetch = value; break;
+    case VFI_OPT_FORCE_PATH: idx->opt_force_path = value; break;
+    case VFI_OPT_PROFILE: idx->opt_profile = value; break;
+    case VFI_OPT_TAU_HINT: idx->opt_tau_hint = value; break;
+    case VFI_OPT_NUM_CTAS: idx->opt_num_ctas = value; break;
+    default: return fail(VFI_ERR_INVALID, "unknown option");
+  }
+  return VFI_OK;
+}
+
+int vfi_index_get_stats(vfi_index_t* idx, vfi_search_stats* out, int reset) {
+  if (!idx || !out) return fail(VFI_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(idx->mu);
+  DeviceGuard guard(idx->device);
+  uint32_t bits = 0;
+  VFI_CUDA(cudaMemcpy(&bits, idx->d_max_err, 4, cudaMemcpyDeviceToHost));
+  float f;
+  std::memcpy(&f, &bits, 4);
+  idx->stats.max_abs_err = f;
+  *out = idx->stats;
+  if (reset) {
+    idx->stats = vfi_search_stats{};
+    VFI_CUDA(cudaMemset(idx->d_max_err, 0, 4));
+  }
+  return VFI_OK;
+}
+
+int vfi_index_reconstruct(vfi_index_t* idx, int64_t i, float* out, int mem) {
+  if (!idx || !out) return fail(VFI_ERR_INVALID, "null argument");
+  if (i < 0 || i >= idx->n) return fail(VFI_ERR_INVALID, "row out of range");
+  std::lock_guard<std::mutex> lock(idx->mu);
+  DeviceGuard guard(idx->device);
+  std::vector<float> row(idx->d);
+  if (idx->store == VFI_STORE_F32) {
+    VFI_CUDA(cudaMemcpy(row.data(), idx->master + i * idx->dp, sizeof(float) * idx->d, cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<uint16_t> h(idx->d);
+    VFI_CUDA(cudaMemcpy(h.data(), idx->g + i * idx->kp, 2 * static_cast<size_t>(idx->d), cudaMemcpyDeviceToHost));
+    for (int j = 0; j < idx->d; ++j) {
+      uint32_t u = static_cast<uint32_t>(h[j]) << 16;
+      std::memcpy(&row[j], &u, 4);
+    }
+  }
+  VFI_CUDA(cudaMemcpy(out, row.data(), sizeof(float) * idx->d, mem == VFI_MEM_DEVICE ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost));
+  return VFI_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// search internals
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+int prep_queries(vfi_index* idx, const float* q_dev, int nq, cudaStream_t st) {
+  VFI_TRY(idx->w_qcanon.ensure(static_cast<size_t>(nq) * idx->dp * 4));
+  VFI_TRY(idx->w_qg.ensure(static_cast<size_t>(nq) * idx->kp * 2));
+  VFI_TRY(idx->w_eps.ensure(static_cast<size_t>(nq) * 4));
+  const int threads = 256;
+  const int blocks = static_cast<int>(ceil_div(static_cast<int64_t>(nq) * 32, threads));
+  if (idx->store == VFI_STORE_F32)
+    vfi::prep_queries_kernel<true><<<blocks, threads, 0, st>>>(q_dev, nq, idx->d, idx->dp, idx->w_qcanon.as<float>(),
+                                                                idx->w_qg.as<uint16_t>(), idx->kp, idx->xnorm_bits,
+                                                                idx->w_eps.as<float>());
+  else
+    vfi::prep_queries_kernel<false><<<blocks, threads, 0, st>>>(q_dev, nq, idx->d, idx->dp, idx->w_qcanon.as<float>(),
+                                                                 idx->w_qg.as<uint16_t>(), idx->kp, idx->xnorm_bits,
+                                                                 idx->w_eps.as<float>());
+  LAUNCHED();
+  VFI_CUDA(cudaGetLastError());
+  return VFI_OK;
+}
+
+// exact canonical scores of ALL rows for the selected queries, then exact top-k (no certificate)
+int exhaustive_pass(vfi_index* idx, const int* qsel_dev, int nsel, int k, float* out_scores, int64_t* out_ids,
+                    cudaStream_t st) {
+  const int64_t n = idx->n;
+  const int64_t per_query = std::max<int64_t>(n, 1) * 8;
+  const int chunk = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nsel, (static_cast<int64_t>(1) << 30) / per_query)));
+  VFI_TRY(idx->w_keys2.ensure(static_cast<size_t>(chunk) * per_query));
+  if (qsel_dev == nullptr) {  // all queries of the batch: identity list
+    std::vector<int> iota(nsel);
+    for (int i = 0; i < nsel; ++i) iota[i] = i;
+    VFI_TRY(idx->w_sel.ensure(static_cast<size_t>(nsel) * 4));
+    VFI_CUDA(cudaMemcpyAsync(idx->w_sel.p, iota.data(), static_cast<size_t>(nsel) * 4, cudaMemcpyHostToDevice, st));
+    VFI_CUDA(cudaStreamSynchronize(st));
+    qsel_dev = idx->w_sel.as<int>();
+  }
+  for (int s0 = 0; s0 < nsel; s0 += chunk) {
+    const int ns = std::min(chunk, nsel - s0);
+    const int* sel = qsel_dev + s0;
+    if (n > 0) {
+      dim3 grid(static_cast<unsigned>(ceil_div(n, 128)), static_cast<unsigned>(ns));
+      if (idx->store == VFI_STORE_F32)
+        vfi::canon_score_kernel<float><<<grid, 128, 0, st>>>(idx->master, idx->dp, idx->dp, idx->w_qcanon.as<float>(), sel,
+                                                             nullptr, nullptr, 0, n, idx->w_keys2.as<uint64_t>(), n, nullptr);
+      else
+        vfi::canon_score_kernel<uint16_t><<<grid, 128, 0, st>>>(idx->g, idx->kp, idx->dp, idx->w_qcanon.as<float>(), sel,
+                                                                nullptr, nullptr, 0, n, idx->w_keys2.as<uint64_t>(), n, nullptr);
+      LAUNCHED();
+      VFI_CUDA(cudaGetLastError());
+    }
+    vfi::finalize_kernel<<<ns, 256, sizeof(vfi::SelectSmem), st>>>(idx->w_keys2.as<uint64_t>(), n, n, sel, nullptr, k,
+                                                                  idx->id_offset, nullptr, nullptr, 0, out_scores, out_ids,
+                                                                  nullptr, nullptr);
+    LAUNCHED();
+    VFI_CUDA(cudaGetLastError());
+  }
+  return VFI_OK;
+}
+
+int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, int64_t ld_scores, const float* tau,
+                 int* o_groups, int* o_nq_pad, int* o_cap, cudaStream_t st) {
+  const int n_mtiles = static_cast<int>(ceil_div(nq, vfi::kBM));
+  int n_ctas = idx->opt_num_ctas > 0 ? static_cast<int>(idx->opt_num_ctas) : idx->num_sms;
+  n_ctas = std::max(n_ctas, n_mtiles);
+  const int n_tiles = static_cast<int>(ceil_div(idx->n, vfi::kBN));
+  int n_groups = std::max(1, n_ctas / n_mtiles);
+  n_groups = std::min(n_groups, std::max(1, n_tiles));
+  const int nq_pad = n_mtiles * vfi::kBM;
+  const int cap = 2 * keep + 32;
+  CUtensorMap tq, td;
+  VFI_TRY(make_tmap(&tq, idx->w_qg.p, nq, idx->kp, idx->kp, vfi::kBM));
+  VFI_TRY(make_tmap(&td, idx->g, idx->n, idx->kp, idx->kp, vfi::kBN));
+  vfi::DenseParams p{};
+  p.nq = nq;
+  p.nq_pad = nq_pad;
+  p.n_rows = static_cast<int>(idx->n);
+  p.n_kblocks = static_cast<int>(idx->kp / vfi::kBK);
+  p.n_mtiles = n_mtiles;
+  p.n_groups = n_groups;
+  p.n_tiles = n_tiles;
+  p.keep = keep;
+  p.cap = cap;
+  p.tau_init = tau;
+  p.scores_out = scores_out;
+  p.ld_scores = ld_scores;
+  if (mode == vfi::MODE_TOPK) {
+    VFI_TRY(idx->w_cand.ensure(static_cast<size_t>(n_groups) * nq_pad * cap * 8));
+    VFI_TRY(idx->w_cand_count.ensure(static_cast<size_t>(n_groups) * nq_pad * 4));
+    p.cand = idx->w_cand.as<uint64_t>();
+    p.cand_count = idx->w_cand_count.as<uint32_t>();
+  }
+  const bool prof = idx->opt_profile != 0;
+  if (prof) cudaEventRecord(idx->ev0, st);
+  const int grid = n_groups * n_mtiles;
+  if (mode == vfi::MODE_TOPK)
+    vfi::dense_fused_kernel<vfi::MODE_TOPK><<<grid, vfi::kDenseThreads, vfi::kDenseSmemBytes, st>>>(tq, td, p);
+  else
+    vfi::dense_fused_kernel<vfi::MODE_STORE><<<grid, vfi::kDenseThreads, vfi::kDenseSmemBytes, st>>>(tq, td, p);
+  LAUNCHED();
+  if (prof) cudaEventRecord(idx->ev1, st);
+  VFI_CUDA(cudaGetLastError());
+  idx->stats.fused_launches++;
+  if (o_groups) *o_groups = n_groups;
+  if (o_nq_pad) *o_nq_pad = nq_pad;
+  if (o_cap) *o_cap = cap;
+  return VFI_OK;
+}
+
+// one batch of <= kMaxQueriesPerLaunch queries already on the device; results to device buffers
+int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+  VFI_TRY(prep_queries(idx, q_dev, nq, st));
+  const int64_t n = idx->n;
+  int keep = idx->opt_overfetch > 0 ? static_cast<int>(idx->opt_overfetch)
+                                    : static_cast<int>(round_up(k + std::max(16, k / 4), 32));
+  keep = std::max(keep, static_cast<int>(round_up(k, 32)));
+  int path = static_cast<int>(idx->opt_force_path);
+  if (path == 0) {
+    if (n <= kExhaustiveRows || keep >= n) path = 1;
+    else if (nq <= vfi::kGemvMaxQ && keep <= kGemvMaxKeep) path = 3;
+    else if (keep <= kFusedMaxKeep) path = 2;
+    else path = 1;
+  }
+  if (path == 2 && (keep > kFusedMaxKeep || n == 0)) path = 1;
+  if (path == 3 && (nq > vfi::kGemvMaxQ || keep > kGemvMaxKeep || n == 0)) path = 1;
+  idx->stats.last_path = path;
+  idx->stats.last_overfetch = keep;
+  if (path == 1) return exhaustive_pass(idx, nullptr, nq, k, out_scores, out_ids, st);
+
+  int n_groups = 0, nq_pad = 0, cap = 0;
+  const float* tau = nullptr;
+  if (path == 2) {
+    VFI_TRY(launch_fused(idx, nq, keep, vfi::MODE_TOPK, nullptr, 0, tau, &n_groups, &nq_pad, &cap, st));
+  } else {
+    // streaming scorer: per-CTA shared key buffers
+    int cap_s = 1;
+    while (cap_s < keep + vfi::kGemvRowsPerRound) cap_s <<= 1;
+    const size_t smem = ((static_cast<size_t>(nq) * idx->dp * 4 + 15) & ~size_t(15)) + static_cast<size_t>(nq) * cap_s * 8 + 256;
+    if (smem > 160 * 1024) return fail(VFI_ERR_UNSUPPORTED, "streaming scorer: query block does not fit shared memory");
+    const int ctas_per_sm = std::max<int>(1, std::min<int>(3, static_cast<int>((200 * 1024) / smem)));
+    n_groups = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(idx->num_sms) * ctas_per_sm,
+                                                  ceil_div(n, vfi::kGemvRowsPerRound)));
+    nq_pad = nq;
+    cap = keep;
+    VFI_TRY(idx->w_cand.ensure(static_cast<size_t>(n_groups) * nq_pad * cap * 8));
+    VFI_TRY(idx->w_cand_count.ensure(static_cast<size_t>(n_groups) * nq_pad * 4));
+    const bool prof = idx->opt_profile != 0;
+    if (prof) cudaEventRecord(idx->ev0, st);
+    if (idx->store == VFI_STORE_F32)
+      vfi::gemv_topk_kernel<float><<<n_groups, vfi::kGemvThreads, smem, st>>>(
+          idx->master, idx->dp, idx->dp, n, idx->w_qcanon.as<float>(), nq, keep, cap_s, idx->w_cand.as<uint64_t>(),
+          idx->w_cand_count.as<uint32_t>(), nq_pad, cap);
+    else
+      vfi::gemv_topk_kernel<uint16_t><<<n_groups, vfi::kGemvThreads, smem, st>>>(
+          idx->g, idx->kp, idx->dp, n, idx->w_qcanon.as<float>(), nq, keep, cap_s, idx->w_cand.as<uint64_t>(),
+          idx->w_cand_count.as<uint32_t>(), nq_pad, cap);
+    LAUNCHED();
+    if (prof) cudaEventRecord(idx->ev1, st);
+    VFI_CUDA(cudaGetLastError());
+    idx->stats.fused_launches++;
+  }
+  // K1c: per-query union of the group buffers
+  VFI_TRY(idx->w_keys.ensure(static_cast<size_t>(nq) * keep * 8));
+  VFI_TRY(idx->w_keys_n.ensure(static_cast<size_t>(nq) * 4));
+  VFI_TRY(idx->w_bound.ensure(static_cast<size_t>(nq) * 4));
+  vfi::cand_reduce_kernel<<<nq, 256, sizeof(vfi::SelectSmem), st>>>(idx->w_cand.as<uint64_t>(), idx->w_cand_count.as<uint32_t>(),
+                                                                   n_groups, nq_pad, cap, keep, tau, idx->w_keys.as<uint64_t>(),
+                                                                   idx->w_keys_n.as<uint32_t>(), idx->w_bound.as<float>());
+  LAUNCHED();
+  VFI_CUDA(cudaGetLastError());
+  // K2a: canonical rescoring of the candidates
+  VFI_TRY(idx->w_keys2.ensure(static_cast<size_t>(nq) * keep * 8));
+  {
+    dim3 grid(static_cast<unsigned>(ceil_div(keep, 128)), static_cast<unsigned>(nq));
+    if (idx->store == VFI_STORE_F32)
+      vfi::canon_score_kernel<float><<<grid, 128, 0, st>>>(idx->master, idx->dp, idx->dp, idx->w_qcanon.as<float>(), nullptr,
+                                                           idx->w_keys.as<uint64_t>(), idx->w_keys_n.as<uint32_t>(), keep, 0,
+                                                           idx->w_keys2.as<uint64_t>(), keep, idx->d_max_err);
+    else
+      vfi::canon_score_kernel<uint16_t><<<grid, 128, 0, st>>>(idx->g, idx->kp, idx->dp, idx->w_qcanon.as<float>(), nullptr,
+                                                              idx->w_keys.as<uint64_t>(), idx->w_keys_n.as<uint32_t>(), keep, 0,
+                                                              idx->w_keys2.as<uint64_t>(), keep, idx->d_max_err);
+    LAUNCHED();
+    VFI_CUDA(cudaGetLastError());
+  }
+  // K2b: final order + certificate
+  VFI_TRY(idx->w_flag.ensure(static_cast<size_t>(kMaxQueriesPerLaunch + 1) * 4));
+  int* d_flag = idx->w_flag.as<int>();
+  VFI_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
+  vfi::finalize_kernel<<<nq, 256, sizeof(vfi::SelectSmem), st>>>(idx->w_keys2.as<uint64_t>(), keep, keep, nullptr,
+                                                                idx->w_keys_n.as<uint32_t>(), k, idx->id_offset,
+                                                                idx->w_bound.as<float>(), idx->w_eps.as<float>(), 1, out_scores,
+                                                                out_ids, d_flag + 1, d_flag);
+  LAUNCHED();
+  VFI_CUDA(cudaGetLastError());
+  VFI_CUDA(cudaMemcpyAsync(idx->h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+  VFI_CUDA(cudaStreamSynchronize(st));
+  if (idx->opt_profile) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, idx->ev0, idx->ev1) == cudaSuccess) {
+      idx->stats.fused_ms_total += ms;
+      idx->stats.fused_ms_samples++;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  const int n_flagged = idx->h_flag[0];
+  if (n_flagged > 0) {
+    idx->stats.retried_queries += n_flagged;
+    VFI_TRY(exhaustive_pass(idx, d_flag + 1, n_flagged, k, out_scores, out_ids, st));
+  }
+  return VFI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vfi_index_search(vfi_index_t* idx, const float* q, int64_t nq, int k, float* out_scores, int64_t* out_ids, int mem,
+                     void* stream) {
+  if (!idx || (nq > 0 && (!q || !out_scores || !out_ids)) || nq < 0) return fail(VFI_ERR_INVALID, "bad argument to vfi_index_search");
+  if (k <= 0) return fail(VFI_ERR_INVALID, "k must be positive");
+  if (k > VFI_MAX_K) return fail(VFI_ERR_UNSUPPORTED, "k exceeds VFI_MAX_K (2048)");
+  if (nq == 0) return VFI_OK;
+  std::lock_guard<std::mutex> lock(idx->mu);
+  DeviceGuard guard(idx->device);
+  if (!guard.ok) return fail(VFI_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  idx->stats.searches++;
+  idx->stats.queries += nq;
+  for (int64_t q0 = 0; q0 < nq; q0 += kMaxQueriesPerLaunch) {
+    const int nb = static_cast<int>(std::min<int64_t>(kMaxQueriesPerLaunch, nq - q0));
+    const float* qd = q + q0 * idx->d;
+    float* os = out_scores + q0 * k;
+    int64_t* oi = out_ids + q0 * k;
+    if (mem == VFI_MEM_HOST) {
+      VFI_TRY(idx->w_qin.ensure(static_cast<size_t>(nb) * idx->d * 4));
+      VFI_TRY(idx->w_out_scores.ensure(static_cast<size_t>(nb) * k * 4));
+      VFI_TRY(idx->w_out_ids.ensure(static_cast<size_t>(nb) * k * 8));
+      VFI_CUDA(cudaMemcpyAsync(idx->w_qin.p, qd, static_cast<size_t>(nb) * idx->d * 4, cudaMemcpyHostToDevice, st));
+      qd = idx->w_qin.as<float>();
+      os = idx->w_out_scores.as<float>();
+      oi = idx->w_out_ids.as<int64_t>();
+    }
+    VFI_TRY(search_batch(idx, qd, nb, k, os, oi, st));
+    if (mem == VFI_MEM_HOST) {
+      VFI_CUDA(cudaMemcpyAsync(out_scores + q0 * k, os, static_cast<size_t>(nb) * k * 4, cudaMemcpyDeviceToHost, st));
+      VFI_CUDA(cudaMemcpyAsync(out_ids + q0 * k, oi, static_cast<size_t>(nb) * k * 8, cudaMemcpyDeviceToHost, st));
+      VFI_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+  return VFI_OK;
+}
+
+int vfi_index_debug_scores(vfi_index_t* idx, const float* q, int64_t nq, float* out, int mem, void* stream) {
+  if (!idx || !q || !out || nq <= 0 || nq > kMaxQueriesPerLaunch) return fail(VFI_ERR_INVALID, "bad argument to vfi_index_debug_scores");
+  if (idx->n == 0) return VFI_OK;
+  std::lock_guard<std::mutex> lock(idx->mu);
+  DeviceGuard guard(idx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float* qd = q;
+  if (mem == VFI_MEM_HOST) {
+    VFI_TRY(idx->w_qin.ensure(static_cast<size_t>(nq) * idx->d * 4));
+    VFI_CUDA(cudaMemcpyAsync(idx->w_qin.p, q, static_cast<size_t>(nq) * idx->d * 4, cudaMemcpyHostToDevice, st));
+    qd = idx->w_qin.as<float>();
+  }
+  VFI_TRY(prep_queries(idx, qd, static_cast<int>(nq), st));
+  const int64_t ld = ceil_div(idx->n, vfi::kBN) * vfi::kBN;
+  const int64_t nq_pad = ceil_div(nq, vfi::kBM) * vfi::kBM;
+  VFI_TRY(idx->w_dbg.ensure(static_cast<size_t>(nq_pad) * ld * 4));
+  VFI_TRY(launch_fused(idx, static_cast<int>(nq), 32, vfi::MODE_STORE, idx->w_dbg.as<float>(), ld, nullptr, nullptr, nullptr, nullptr, st));
+  VFI_CUDA(cudaMemcpy2DAsync(out, static_cast<size_t>(idx->n) * 4, idx->w_dbg.p, static_cast<size_t>(ld) * 4,
+                             static_cast<size_t>(idx->n) * 4, static_cast<size_t>(nq),
+                             mem == VFI_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+  VFI_CUDA(cudaStreamSynchronize(st));
+  return VFI_OK;
+}
+
+int vfi_normalize_l2(float* x, int64_t n, int d, int mem, int device, void* stream) {
+  if ((!x && n > 0) || n < 0 || d <= 0) return fail(VFI_ERR_INVALID, "bad argument to vfi_normalize_l2");
+  if (n == 0) return VFI_OK;
+  cudaDeviceProp prop;
+  VFI_TRY(device_props(device, &prop));
+  DeviceGuard guard(device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t chunk = std::max<int64_t>(1, (static_cast<int64_t>(256) << 20) / (static_cast<int64_t>(d) * 4));
+  float* stage = nullptr;
+  if (mem == VFI_MEM_HOST) VFI_CUDA(cudaMalloc(&stage, static_cast<size_t>(std::min(chunk, n)) * d * 4));
+  int rc = VFI_OK;
+  for (int64_t r0 = 0; r0 < n && rc == VFI_OK; r0 += chunk) {
+    const int64_t rows = std::min(chunk, n - r0);
+    float* p = x + r0 * d;
+    float* dp = p;
+    if (mem == VFI_MEM_HOST) {
+      if (cudaMemcpyAsync(stage, p, static_cast<size_t>(rows) * d * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = fail(VFI_ERR_CUDA, "H2D copy failed"); break; }
+      dp = stage;
+    }
+    vfi::normalize_l2_kernel<<<static_cast<unsigned>(ceil_div(rows * 32, 256)), 256, 0, st>>>(dp, rows, d);
+    LAUNCHED();
+    if (mem == VFI_MEM_HOST) {
+      if (cudaMemcpyAsync(p, stage, static_cast<size_t>(rows) * d * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = fail(VFI_ERR_CUDA, "D2H copy failed"); break; }
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(VFI_ERR_CUDA, std::string("normalize_l2: ") + cudaGetErrorString(e));
+  }
+  if (stage) cudaFree(stage);
+  return rc;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// small helpers shared by merge / fusion / cosine entry points: stage host buffers on the device
+// =============================================================================================
+namespace {
+
+struct Staged {
+  std::vector<void*> to_free;
+  ~Staged() {
+    for (void* p : to_free) cudaFree(p);
+  }
+  template <class T>
+  int in(const T* src, size_t count, int mem, cudaStream_t st, const T** out) {
+    if (mem == VFI_MEM_DEVICE) { *out = src; return VFI_OK; }
+    void* p = nullptr;
+    VFI_CUDA(cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16)));
+    to_free.push_back(p);
+    VFI_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    *out = reinterpret_cast<const T*>(p);
+    return VFI_OK;
+  }
+  template <class T>
+  int out(T* dst, size_t count, int mem, T** dev) {
+    if (mem == VFI_MEM_DEVICE) { *dev = dst; return VFI_OK; }
+    void* p = nullptr;
+    VFI_CUDA(cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16)));
+    to_free.push_back(p);
+    *dev = reinterpret_cast<T*>(p);
+    return VFI_OK;
+  }
+  template <class T>
+  int back(T* dst, const T* dev, size_t count, int mem, cudaStream_t st) {
+    if (mem == VFI_MEM_DEVICE) return VFI_OK;
+    VFI_CUDA(cudaMemcpyAsync(dst, dev, count * sizeof(T), cudaMemcpyDeviceToHost, st));
+    return VFI_OK;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int vfi_merge_topk(const float* scores, const int64_t* ids, int g, int64_t nq, int k_in, int k_out, float* out_scores,
+                   int64_t* out_ids, int mem, int device, void* stream) {
+  if (!scores || !ids || !out_scores || !out_ids || g <= 0 || nq < 0 || k_in <= 0 || k_out <= 0)
+    return fail(VFI_ERR_INVALID, "bad argument to vfi_merge_topk");
+  if (k_out > VFI_MAX_K) return fail(VFI_ERR_UNSUPPORTED, "k_out exceeds VFI_MAX_K");
+  if (nq == 0) return VFI_OK;
+  cudaDeviceProp prop;
+  VFI_TRY(device_props(device, &prop));
+  DeviceGuard guard(device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Staged sg;
+  const size_t n_in = static_cast<size_t>(g) * nq * k_in, n_out = static_cast<size_t>(nq) * k_out;
+  const float* ds;
+  const int64_t* di;
+  float* os;
+  int64_t* oi;
+  VFI_TRY(sg.in(scores, n_in, mem, st, &ds));
+  VFI_TRY(sg.in(ids, n_in, mem, st, &di));
+  VFI_TRY(sg.out(out_scores, n_out, mem, &os));
+  VFI_TRY(sg.out(out_ids, n_out, mem, &oi));
+  vfi::merge_kernel<<<static_cast<unsigned>(nq), 256, sizeof(vfi::SelectSmem), st>>>(ds, di, g, nq, k_in, k_out, os, oi);
+  LAUNCHED();
+  VFI_CUDA(cudaGetLastError());
+  VFI_TRY(sg.back(out_scores, os, n_out, mem, st));
+  VFI_TRY(sg.back(out_ids, oi, n_out, mem, st));
+  if (mem == VFI_MEM_HOST) VFI_CUDA(cudaStreamSynchronize(st));
+  return VFI_OK;
+}
+
+int vfi_fuse_rrf(const int64_t* ids, int64_t nq, int n_paths, int depth, float k_rrf, int k, float* out_scores,
+                 int64_t* out_ids, int mem, int device, void* stream) {
+  if (!ids || !out_scores || !out_ids || nq < 0 || n_paths <= 0 || depth <= 0 || k <= 0)
+    return fail(VFI_ERR_INVALID, "bad argument to vfi_fuse_rrf");
+  if (static_cast<int64_t>(n_paths) * depth > vfi::kSortCap) return fail(VFI_ERR_UNSUPPORTED, "n_paths*depth exceeds 4096");
+  if (nq == 0) return VFI_OK;
+  cudaDeviceProp prop;
+  VFI_TRY(device_props(device, &prop));
+  DeviceGuard guard(device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Staged sg;
+  const size_t n_in = static_cast<size_t>(nq) * n_paths * depth, n_out = static_cast<size_t>(nq) * k;
+  const int64_t* di;
+  float* os;
+  int64_t* oi;
+  VFI_TRY(sg.in(ids, n_in, mem, st, &di));
+  VFI_TRY(sg.out(out_scores, n_out, mem, &os));
+  VFI_TRY(sg.out(out_ids, n_out, mem, &oi));
+  vfi::rrf_kernel<<<static_cast<unsigned>(nq), 256, sizeof(vfi::SelectSmem), st>>>(di, n_paths, depth, k_rrf, k, os, oi);
+  LAUNCHED();
+  VFI_CUDA(cudaGetLastError());
+  VFI_TRY(sg.back(out_scores, os, n_out, mem, st));
+  VFI_TRY(sg.back(out_ids, oi, n_out, mem, st));
+  if (mem == VFI_MEM_HOST) VFI_CUDA(cudaStreamSynchronize(st));
+  return VFI_OK;
+}
+
+int vfi_fuse_union(const int64_t* ids, const float* scores, int64_t nq, int n_paths, int depth, int64_t* out_ids,
+                   float* out_scores, int32_t* out_path, int32_t* out_count, int mem, int device, void* stream) {
+  if (!ids || !scores || !out_ids || !out_scores || !out_path || !out_count || nq < 0 || n_paths <= 0 || depth <= 0)
+    return fail(VFI_ERR_INVALID, "bad argument to vfi_fuse_union");
+  if (static_cast<int64_t>(n_paths) * depth > vfi::kSortCap) return fail(VFI_ERR_UNSUPPORTED, "n_paths*depth exceeds 4096");
+  if (nq == 0) return VFI_OK;
+  cudaDeviceProp prop;
+  VFI_TRY(device_props(device, &prop));
+  DeviceGuard guard(device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Staged sg;
+  const size_t n_in = static_cast<size_t>(nq) * n_paths * depth;
+  const int64_t* di;
+  const float* ds;
+  int64_t* oi;
+  float* os;
+  int32_t *op, *oc;
+  VFI_TRY(sg.in(ids, n_in, mem, st, &di));
+  VFI_TRY(sg.in(scores, n_in, mem, st, &ds));
+  VFI_TRY(sg.out(out_ids, n_in, mem, &oi));
+  VFI_TRY(sg.out(out_scores, n_in, mem, &os));
+  VFI_TRY(sg.out(out_path, n_in, mem, &op));
+  VFI_TRY(sg.out(out_count, static_cast<size_t>(nq), mem, &oc));
+  vfi::union_kernel<<<static_cast<unsigned>(nq), 256, sizeof(vfi::SelectSmem), st>>>(di, ds, n_paths, depth, oi, os, op, oc);
+  LAUNCHED();
+  VFI_CUDA(cudaGetLastError());
+  VFI_TRY(sg.back(out_ids, oi, n_in, mem, st));
+  VFI_TRY(sg.back(out_scores, os, n_in, mem, st));
+  VFI_TRY(sg.back(out_path, op, n_in, mem, st));
+  VFI_TRY(sg.back(out_count, oc, static_cast<size_t>(nq), mem, st));
+  if (mem == VFI_MEM_HOST) VFI_CUDA(cudaStreamSynchronize(st));
+  return VFI_OK;
+}
+
+// cosine top-k of the experiment scripts: normalise both sides, exhaustive exact scores, then the
+// argsort()[-k:][::-1] order = (score desc, index DESC).  Implemented on top of a temporary
+// F32 index by mapping index i -> n_c-1-i so that "higher index first" becomes "lower id first".
+int vfi_cosine_topk(const float* e, int64_t n_e, const float* c, int64_t n_c, int d, int k, float* out_scores,
+                    int64_t* out_ids, int mem, int device, void* stream) {
+  if (!e || !c || !out_scores || !out_ids || n_e < 0 || n_c < 0 || d <= 0 || k <= 0)
+    return fail(VFI_ERR_INVALID, "bad argument to vfi_cosine_topk");
+  if (mem != VFI_MEM_HOST) return fail(VFI_ERR_UNSUPPORTED, "vfi_cosine_topk takes host buffers");
+  if (n_e == 0) return VFI_OK;
+  std::vector<float> cn(static_cast<size_t>(n_c) * d), en(e, e + static_cast<size_t>(n_e) * d);
+  for (int64_t i = 0; i < n_c; ++i)
+    std::memcpy(&cn[static_cast<size_t>(n_c - 1 - i) * d], c + static_cast<size_t>(i) * d, sizeof(float) * d);
+  VFI_TRY(vfi_normalize_l2(cn.data(), n_c, d, VFI_MEM_HOST, device, stream));
+  VFI_TRY(vfi_normalize_l2(en.data(), n_e, d, VFI_MEM_HOST, device, stream));
+  vfi_index_t* idx = nullptr;
+  VFI_TRY(vfi_index_create(d, VFI_STORE_F32, device, &idx));
+  int rc = vfi_index_add(idx, cn.data(), n_c, VFI_MEM_HOST, stream);
+  if (rc == VFI_OK) rc = vfi_index_search(idx, en.data(), n_e, k, out_scores, out_ids, VFI_MEM_HOST, stream);
+  vfi_index_destroy(idx);
+  if (rc != VFI_OK) return rc;
+  for (int64_t i = 0; i < n_e * k; ++i)
+    if (out_ids[i] >= 0) out_ids[i] = n_c - 1 - out_ids[i];
+  return VFI_OK;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// BM25
+// =============================================================================================
+struct vfi_bm25 {
+  int device = 0, num_sms = 148;
+  int64_t n_vocab = 0, n_docs = 0, nnz = 0, id_offset = 0;
+  int all_positive = 1;
+  int64_t* indptr = nullptr;
+  int32_t* indices = nullptr;
+  float* data = nullptr;
+  std::vector<int64_t> h_indptr;  // host copy: df lookups for stats and validation
+  DevBuf w_tok, w_qptr, w_cand, w_cand_count, w_keys, w_keys_n, w_bound, w_out_scores, w_out_ids, w_ctr, w_dump, w_sort;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int profile = 0;
+  vfi_bm25_stats stats{};
+  std::mutex mu;
+};
+
+extern "C" {
+
+int vfi_bm25_create(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_vocab, int64_t n_docs,
+                    int64_t id_offset, int device, vfi_bm25_t** out) {
+  if (!out) return fail(VFI_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (!indptr || n_vocab < 0 || n_docs < 0 || id_offset < 0) return fail(VFI_ERR_INVALID, "bad argument to vfi_bm25_create");
+  const int64_t nnz = indptr[n_vocab];
+  if (nnz < 0 || (nnz > 0 && (!indices || !data))) return fail(VFI_ERR_INVALID, "bad posting arrays");
+  if (n_docs >= 0x7FFFFFF0ll) return fail(VFI_ERR_UNSUPPORTED, "a BM25 shard holds at most 2^31-16 docs");
+  for (int64_t t = 0; t < n_vocab; ++t)
+    if (indptr[t] > indptr[t + 1]) return fail(VFI_ERR_INVALID, "indptr must be non-decreasing");
+  cudaDeviceProp prop;
+  VFI_TRY(device_props(device, &prop));
+  DeviceGuard guard(device);
+  vfi_bm25* b = new vfi_bm25();
+  b->device = device;
+  b->num_sms = prop.multiProcessorCount;
+  b->n_vocab = n_vocab;
+  b->n_docs = n_docs;
+  b->nnz = nnz;
+  b->id_offset = id_offset;
+  b->h_indptr.assign(indptr, indptr + n_vocab + 1);
+  float mn = 1.f;
+  for (int64_t i = 0; i < nnz; ++i) mn = std::min(mn, data[i]);
+  b->all_positive = (mn > 0.f) ? 1 : 0;
+  auto bail = [&](int code) {
+    vfi_bm25_destroy(b);
+    return code;
+  };
+  if (cudaMalloc(&b->indptr, sizeof(int64_t) * (n_vocab + 1)) != cudaSuccess ||
+      cudaMalloc(&b->indices, std::max<size_t>(16, sizeof(int32_t) * nnz)) != cudaSuccess ||
+      cudaMalloc(&b->data, std::max<size_t>(16, sizeof(float) * nnz)) != cudaSuccess)
+    return bail(fail(VFI_ERR_NOMEM, "cudaMalloc postings failed"));
+  cudaMemcpy(b->indptr, indptr, sizeof(int64_t) * (n_vocab + 1), cudaMemcpyHostToDevice);
+  if (nnz > 0) {
+    cudaMemcpy(b->indices, indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice);
+    cudaMemcpy(b->data, data, sizeof(float) * nnz, cudaMemcpyHostToDevice);
+  }
+  cudaEventCreate(&b->ev0);
+  cudaEventCreate(&b->ev1);
+  cudaFuncSetAttribute(vfi::bm25_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return bail(fail(VFI_ERR_CUDA, std::string("bm25 setup: ") + cudaGetErrorString(e)));
+  *out = b;
+  return VFI_OK;
+}
+
+int vfi_bm25_destroy(vfi_bm25_t* b) {
+  if (!b) return VFI_OK;
+  DeviceGuard guard(b->device);
+  cudaDeviceSynchronize();
+  if (b->indptr) cudaFree(b->indptr);
+  if (b->indices) cudaFree(b->indices);
+  if (b->data) cudaFree(b->data);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  for (DevBuf* w : {&b->w_tok, &b->w_qptr, &b->w_cand, &b->w_cand_count, &b->w_keys, &b->w_keys_n, &b->w_bound,
+                    &b->w_out_scores, &b->w_out_ids, &b->w_ctr, &b->w_dump, &b->w_sort})
+    w->release();
+  cudaGetLastError();
+  delete b;
+  return VFI_OK;
+}
+
+int64_t vfi_bm25_ndocs(const vfi_bm25_t* b) { return b ? b->n_docs : 0; }
+
+int vfi_bm25_set_profile(vfi_bm25_t* b, int on) {
+  if (!b) return fail(VFI_ERR_INVALID, "null argument");
+  b->profile = on;
+  return VFI_OK;
+}
+
+int vfi_bm25_get_stats(vfi_bm25_t* b, vfi_bm25_stats* out, int reset) {
+  if (!b || !out) return fail(VFI_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(b->mu);
+  *out = b->stats;
+  if (reset) b->stats = vfi_bm25_stats{};
+  return VFI_OK;
+}
+
+static int bm25_validate_tokens(vfi_bm25* b, const int32_t* q_tokens, const int64_t* q_indptr, int64_t nq, int64_t* bytes) {
+  int64_t total = 0;
+  for (int64_t q = 0; q < nq; ++q) {
+    const int64_t t0 = q_indptr[q], t1 = q_indptr[q + 1];
+    if (t1 < t0) return fail(VFI_ERR_INVALID, "q_indptr must be non-decreasing");
+    if (t1 - t0 > vfi::kBmMaxTok) return fail(VFI_ERR_UNSUPPORTED, "a query has more than 64 tokens");
+    for (int64_t i = t0; i < t1; ++i) {
+      const int32_t t = q_tokens[i];
+      if (t < 0 || t >= b->n_vocab) return fail(VFI_ERR_INVALID, "token id out of range (drop unknown tokens before the call)");
+      total += (b->h_indptr[t + 1] - b->h_indptr[t]) * 8;
+    }
+  }
+  *bytes = total;
+  return VFI_OK;
+}
+
+int vfi_bm25_search(vfi_bm25_t* b, const int32_t* q_tokens, const int64_t* q_indptr, int64_t nq, int k, float* out_scores,
+                    int64_t* out_ids, int mem, void* stream) {
+  if (!b || !q_indptr || nq < 0 || (nq > 0 && (!out_scores || !out_ids))) return fail(VFI_ERR_INVALID, "bad argument to vfi_bm25_search");
+  if (k <= 0) return fail(VFI_ERR_INVALID, "k must be positive");
+  if (k > VFI_MAX_K / 2) return fail(VFI_ERR_UNSUPPORTED, "bm25 top-k supports k <= 1024 (use vfi_bm25_score_all for k = N)");
+  if (nq == 0) return VFI_OK;
+  if (mem != VFI_MEM_HOST) return fail(VFI_ERR_UNSUPPORTED, "vfi_bm25_search takes host token buffers and host outputs");
+  std::lock_guard<std::mutex> lock(b->mu);
+  DeviceGuard guard(b->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t bytes = 0;
+  VFI_TRY(bm25_validate_tokens(b, q_tokens, q_indptr, nq, &bytes));
+  b->stats.postings_bytes = bytes;
+  const int64_t n_tok = q_indptr[nq];
+  const int keep = static_cast<int>(round_up(k, 32));
+  int cap = 1;
+  while (cap < keep + vfi::kBmScan) cap <<= 1;
+  const size_t smem = ((sizeof(vfi::Bm25Smem) + 15) & ~size_t(15)) + static_cast<size_t>(cap) * 8;
+  const int n_ctas = b->num_sms * 2;
+  const int64_t n_tiles = std::max<int64_t>(1, ceil_div(b->n_docs, vfi::kBmTile));
+  int64_t n_seg = std::min<int64_t>(n_tiles, std::max<int64_t>(1, ceil_div(static_cast<int64_t>(8) * n_ctas, nq)));
+  const int64_t seg_docs = ceil_div(n_tiles, n_seg) * vfi::kBmTile;
+  n_seg = std::max<int64_t>(1, ceil_div(b->n_docs, seg_docs));
+  VFI_TRY(b->w_tok.ensure(std::max<size_t>(16, static_cast<size_t>(n_tok) * 4)));
+  VFI_TRY(b->w_qptr.ensure(static_cast<size_t>(nq + 1) * 8));
+  VFI_TRY(b->w_cand.ensure(static_cast<size_t>(n_seg) * nq * keep * 8));
+  VFI_TRY(b->w_cand_count.ensure(static_cast<size_t>(n_seg) * nq * 4));
+  VFI_TRY(b->w_keys.ensure(static_cast<size_t>(nq) * keep * 8));
+  VFI_TRY(b->w_keys_n.ensure(static_cast<size_t>(nq) * 4));
+  VFI_TRY(b->w_bound.ensure(static_cast<size_t>(nq) * 4));
+  VFI_TRY(b->w_out_scores.ensure(static_cast<size_t>(nq) * k * 4));
+  VFI_TRY(b->w_out_ids.ensure(static_cast<size_t>(nq) * k * 8));
+  VFI_TRY(b->w_ctr.ensure(16));
+  if (n_tok > 0) VFI_CUDA(cudaMemcpyAsync(b->w_tok.p, q_tokens, static_cast<size_t>(n_tok) * 4, cudaMemcpyHostToDevice, st));
+  VFI_CUDA(cudaMemcpyAsync(b->w_qptr.p, q_indptr, static_cast<size_t>(nq + 1) * 8, cudaMemcpyHostToDevice, st));
+  VFI_CUDA(cudaMemsetAsync(b->w_ctr.p, 0, 16, st));
+  VFI_CUDA(cudaMemsetAsync(b->w_cand_count.p, 0, static_cast<size_t>(n_seg) * nq * 4, st));
+  vfi::Bm25Params p{};
+  p.indptr = b->indptr;
+  p.indices = b->indices;
+  p.data = b->data;
+  p.n_docs = b->n_docs;
+  p.n_seg = static_cast<int>(n_seg);
+  p.seg_docs = seg_docs;
+  p.q_tokens = b->w_tok.as<int32_t>();
+  p.q_indptr = b->w_qptr.as<int64_t>();
+  p.nq = static_cast<int>(nq);
+  p.nq_pad = static_cast<int>(nq);
+  p.keep = keep;
+  p.cap = cap;
+  p.all_positive = b->all_positive;
+  p.cand = b->w_cand.as<uint64_t>();
+  p.cand_count = b->w_cand_count.as<uint32_t>();
+  p.work_counter = b->w_ctr.as<uint32_t>();
+  p.dump = nullptr;
+  const int grid = static_cast<int>(std::min<int64_t>(n_ctas, nq * n_seg));
+  if (b->profile) cudaEventRecord(b->ev0, st);
+  vfi::bm25_kernel<<<grid, vfi::kBmThreads, smem, st>>>(p);
+  LAUNCHED();
+  if (b->profile) cudaEventRecord(b->ev1, st);
+  VFI_CUDA(cudaGetLastError());
+  b->stats.launches++;
+  vfi::cand_reduce_kernel<<<static_cast<unsigned>(nq), 256, sizeof(vfi::SelectSmem), st>>>(
+      b->w_cand.as<uint64_t>(), b->w_cand_count.as<uint32_t>(), static_cast<int>(n_seg), static_cast<int>(nq), keep, keep, nullptr,
+      b->w_keys.as<uint64_t>(), b->w_keys_n.as<uint32_t>(), b->w_bound.as<float>());
+  LAUNCHED();
+  vfi::finalize_kernel<<<static_cast<unsigned>(nq), 256, sizeof(vfi::SelectSmem), st>>>(
+      b->w_keys.as<uint64_t>(), keep, keep, nullptr, b->w_keys_n.as<uint32_t>(), k, b->id_offset, nullptr, nullptr, 0,
+      b->w_out_scores.as<float>(), b->w_out_ids.as<int64_t>(), nullptr, nullptr);
+  LAUNCHED();
+  if (b->all_positive) {
+    vfi::bm25_zero_fill_kernel<<<static_cast<unsigned>(ceil_div(nq, 128)), 128, 0, st>>>(
+        b->w_out_scores.as<float>(), b->w_out_ids.as<int64_t>(), static_cast<int>(nq), k, b->n_docs, b->id_offset);
+    LAUNCHED();
+  }
+  VFI_CUDA(cudaGetLastError());
+  VFI_CUDA(cudaMemcpyAsync(out_scores, b->w_out_scores.p, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));
+  VFI_CUDA(cudaMemcpyAsync(out_ids, b->w_out_ids.p, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, st));
+  VFI_CUDA(cudaStreamSynchronize(st));
+  if (b->profile) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) == cudaSuccess) {
+      b->stats.score_ms_total += ms;
+      b->stats.score_ms_samples++;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  return VFI_OK;
+}
+
+int vfi_bm25_score_all(vfi_bm25_t* b, const int32_t* q_tokens, int64_t n_tokens, float* out, int mem, void* stream) {
+  if (!b || !out || n_tokens < 0 || (n_tokens > 0 && !q_tokens)) return fail(VFI_ERR_INVALID, "bad argument to vfi_bm25_score_all");
+  std::lock_guard<std::mutex> lock(b->mu);
+  DeviceGuard guard(b->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t qptr[2] = {0, n_tokens};
+  int64_t bytes = 0;
+  VFI_TRY(bm25_validate_tokens(b, q_tokens, qptr, 1, &bytes));
+  if (b->n_docs == 0) return VFI_OK;
+  int cap = 2048;
+  const size_t smem = ((sizeof(vfi::Bm25Smem) + 15) & ~size_t(15)) + static_cast<size_t>(cap) * 8;
+  const int n_ctas = b->num_sms * 2;
+  const int64_t n_tiles = std::max<int64_t>(1, ceil_div(b->n_docs, vfi::kBmTile));
+  int64_t n_seg = std::min<int64_t>(n_tiles, n_ctas);
+  const int64_t seg_docs = ceil_div(n_tiles, n_seg) * vfi::kBmTile;
+  n_seg = std::max<int64_t>(1, ceil_div(b->n_docs, seg_docs));
+  VFI_TRY(b->w_tok.ensure(std::max<size_t>(16, static_cast<size_t>(n_tokens) * 4)));
+  VFI_TRY(b->w_qptr.ensure(16));
+  VFI_TRY(b->w_ctr.ensure(16));
+  float* dump = out;
+  if (mem == VFI_MEM_HOST) {
+    VFI_TRY(b->w_dump.ensure(static_cast<size_t>(b->n_docs) * 4));
+    dump = b->w_dump.as<float>();
+  }
+  if (n_tokens > 0) VFI_CUDA(cudaMemcpyAsync(b->w_tok.p, q_tokens, static_cast<size_t>(n_tokens) * 4, cudaMemcpyHostToDevice, st));
+  VFI_CUDA(cudaMemcpyAsync(b->w_qptr.p, qptr, 16, cudaMemcpyHostToDevice, st));
+  VFI_CUDA(cudaMemsetAsync(b->w_ctr.p, 0, 16, st));
+  vfi::Bm25Params p{};
+  p.indptr = b->indptr;
+  p.indices = b->indices;
+  p.data = b->data;
+  p.n_docs = b->n_docs;
+  p.n_seg = static_cast<int>(n_seg);
+  p.seg_docs = seg_docs;
+  p.q_tokens = b->w_tok.as<int32_t>();
+  p.q_indptr = b->w_qptr.as<int64_t>();
+  p.nq = 1;
+  p.nq_pad = 1;
+  p.keep = 32;
+  p.cap = cap;
+  p.all_positive = b->all_positive;
+  p.cand = nullptr;
+  p.cand_count = nullptr;
+  p.work_counter = b->w_ctr.as<uint32_t>();
+  p.dump = dump;
+  vfi::bm25_kernel<<<static_cast<int>(std::min<int64_t>(n_ctas, n_seg)), vfi::kBmThreads, smem, st>>>(p);
+  LAUNCHED();
+  VFI_CUDA(cudaGetLastError());
+  if (mem == VFI_MEM_HOST) VFI_CUDA(cudaMemcpyAsync(out, dump, static_cast<size_t>(b->n_docs) * 4, cudaMemcpyDeviceToHost, st));
+  VFI_CUDA(cudaStreamSynchronize(st));
+  return VFI_OK;
+}
+
+
+}  // extern "C"
+
+namespace vfi {
+__global__ void scores_to_keys_kernel(const float* __restrict__ s, int64_t n, uint64_t* __restrict__ keys) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = make_key(s[i], static_cast<uint32_t>(i));
+}
+__global__ void keys_to_ranked_kernel(const uint64_t* __restrict__ keys, int64_t n, int64_t id_offset,
+                                      float* __restrict__ scores, int64_t* __restrict__ ids) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    scores[i] = key_score(keys[i]);
+    ids[i] = static_cast<int64_t>(key_id(keys[i])) + id_offset;
+  }
+}
+}  // namespace vfi
+
+extern "C" int vfi_bm25_rank_all(vfi_bm25_t* b, const int32_t* q_tokens, int64_t n_tokens, float* out_scores,
+                                 int64_t* out_ids, void* stream) {
+  if (!b || !out_scores || !out_ids) return fail(VFI_ERR_INVALID, "bad argument to vfi_bm25_rank_all");
+  const int64_t n = b->n_docs;
+  if (n == 0) return VFI_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DevBuf scores, keys_in, keys_out, tmp, ids;
+  struct Cleanup {
+    std::vector<DevBuf*> v;
+    ~Cleanup() { for (DevBuf* d : v) d->release(); }
+  } cleanup{{&scores, &keys_in, &keys_out, &tmp, &ids}};
+  {
+    DeviceGuard guard(b->device);
+    VFI_TRY(scores.ensure(static_cast<size_t>(n) * 4));
+  }
+  VFI_TRY(vfi_bm25_score_all(b, q_tokens, n_tokens, scores.as<float>(), VFI_MEM_DEVICE, stream));
+  std::lock_guard<std::mutex> lock(b->mu);
+  DeviceGuard guard(b->device);
+  VFI_TRY(keys_in.ensure(static_cast<size_t>(n) * 8));
+  VFI_TRY(keys_out.ensure(static_cast<size_t>(n) * 8));
+  VFI_TRY(ids.ensure(static_cast<size_t>(n) * 8));
+  const unsigned blocks = static_cast<unsigned>(ceil_div(n, 256));
+  vfi::scores_to_keys_kernel<<<blocks, 256, 0, st>>>(scores.as<float>(), n, keys_in.as<uint64_t>());
+  LAUNCHED();
+  size_t tmp_bytes = 0;
+  VFI_CUDA(cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, keys_in.as<uint64_t>(), keys_out.as<uint64_t>(), n, 0, 64, st));
+  VFI_TRY(tmp.ensure(tmp_bytes));
+  VFI_CUDA(cub::DeviceRadixSort::SortKeysDescending(tmp.p, tmp_bytes, keys_in.as<uint64_t>(), keys_out.as<uint64_t>(), n, 0, 64, st));
+  vfi::keys_to_ranked_kernel<<<blocks, 256, 0, st>>>(keys_out.as<uint64_t>(), n, b->id_offset, scores.as<float>(), ids.as<int64_t>());
+  LAUNCHED();
+  VFI_CUDA(cudaGetLastError());
+  VFI_CUDA(cudaMemcpyAsync(out_scores, scores.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, st));
+  VFI_CUDA(cudaMemcpyAsync(out_ids, ids.p, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, st));
+  VFI_CUDA(cudaStreamSynchronize(st));
+  return VFI_OK;
+}

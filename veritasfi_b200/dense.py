@@ -1,0 +1,140 @@
+"""Torch-facing dense index: the batch entry `search_batch(Q, k) -> (ids, scores)` of SURVEY.md §8b.
+
+Device tensors go straight through the C ABI by pointer (no host round trip); torch is only the
+owner of device memory and streams here.  Reference seam: FaissRetriever.invoke
+(/root/reference/src/utils/faissRetriever.py:28-38) returns (indices, distances) — ids first."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+_FLT_MAX = float(np.finfo(np.float32).max)
+
+
+def _stream_ptr(device: torch.device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class DenseIndex:
+    """Flat inner-product index over a corpus shard resident in HBM.
+
+    store="bf16": the corpus (and the queries) are defined as their bf16 roundings — BASELINE
+    configs 2/3/5.  store="f32": faiss.IndexFlatIP semantics on fp32 values."""
+
+    def __init__(self, d: int, store: str = "bf16", device: int | torch.device = 0, id_offset: int = 0):
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.d = int(d)
+        self.store = store
+        self._h = C.c_void_p()
+        code = {"bf16": N.STORE_BF16, "f32": N.STORE_F32}[store]
+        N.check(N.load().vfi_index_create(self.d, code, self.device.index or 0, C.byref(self._h)))
+        if id_offset:
+            self.set_id_offset(id_offset)
+
+    @property
+    def ntotal(self) -> int:
+        return int(N.load().vfi_index_ntotal(self._h))
+
+    def set_id_offset(self, off: int) -> None:
+        N.check(N.load().vfi_index_set_id_offset(self._h, int(off)))
+
+    def reserve(self, n: int) -> None:
+        N.check(N.load().vfi_index_reserve(self._h, int(n)))
+
+    def set_option(self, opt: int, value: int) -> None:
+        N.check(N.load().vfi_index_set_option(self._h, opt, int(value)))
+
+    def stats(self, reset: bool = False) -> N.SearchStats:
+        st = N.SearchStats()
+        N.check(N.load().vfi_index_get_stats(self._h, C.byref(st), int(reset)))
+        return st
+
+    def add(self, x) -> None:
+        """Append rows.  x: numpy float32 [n,d] (host), or torch float32/bfloat16 [n,d] (cuda or cpu)."""
+        lib = N.load()
+        if isinstance(x, np.ndarray):
+            if x.dtype != np.float32 or x.ndim != 2 or x.shape[1] != self.d or not x.flags.c_contiguous:
+                raise ValueError("add: need a C-contiguous float32 [n, d] array")
+            N.check(lib.vfi_index_add(self._h, x.ctypes.data_as(C.c_void_p), x.shape[0], N.MEM_HOST, None))
+            return
+        if not isinstance(x, torch.Tensor) or x.dim() != 2 or x.shape[1] != self.d:
+            raise ValueError("add: need a [n, d] tensor")
+        x = x.contiguous()
+        mem = N.MEM_DEVICE if x.is_cuda else N.MEM_HOST
+        if x.is_cuda and x.device != self.device:
+            raise ValueError("add: tensor is on another device")
+        stream = _stream_ptr(self.device) if x.is_cuda else None
+        if x.dtype == torch.float32:
+            N.check(lib.vfi_index_add(self._h, C.c_void_p(x.data_ptr()), x.shape[0], mem, stream))
+        elif x.dtype == torch.bfloat16:
+            N.check(lib.vfi_index_add_bf16(self._h, C.c_void_p(x.data_ptr()), x.shape[0], mem, stream))
+        else:
+            raise ValueError("add: dtype must be float32 or bfloat16")
+
+    def search_batch(self, q: torch.Tensor, k: int):
+        """q: float32 [B,d] on this index's GPU.  Returns (ids int64 [B,k], scores float32 [B,k]) on the GPU."""
+        if not (isinstance(q, torch.Tensor) and q.is_cuda and q.dtype == torch.float32 and q.dim() == 2
+                and q.shape[1] == self.d):
+            raise ValueError("search_batch: need a float32 [B, d] cuda tensor")
+        q = q.contiguous()
+        B = q.shape[0]
+        ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
+        scores = torch.empty((B, k), dtype=torch.float32, device=self.device)
+        if B:
+            N.check(N.load().vfi_index_search(self._h, C.c_void_p(q.data_ptr()), B, int(k),
+                                              C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()),
+                                              N.MEM_DEVICE, _stream_ptr(self.device)))
+        return ids, scores
+
+    def search_host(self, q: np.ndarray, k: int):
+        """Host in, host out (pinned or pageable numpy): the reference-facing call, copies included."""
+        if q.dtype != np.float32 or q.ndim != 2 or q.shape[1] != self.d or not q.flags.c_contiguous:
+            raise ValueError("search_host: need a C-contiguous float32 [B, d] array")
+        B = q.shape[0]
+        scores = np.full((B, k), -_FLT_MAX, dtype=np.float32)
+        ids = np.full((B, k), -1, dtype=np.int64)
+        if B:
+            N.check(N.load().vfi_index_search(self._h, q.ctypes.data_as(C.c_void_p), B, int(k),
+                                              scores.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p),
+                                              N.MEM_HOST, None))
+        return ids, scores
+
+    def search_host_into(self, q_ptr: int, B: int, k: int, scores_ptr: int, ids_ptr: int) -> None:
+        """Same as search_host on caller-owned (e.g. pinned) buffers given by address."""
+        N.check(N.load().vfi_index_search(self._h, C.c_void_p(q_ptr), B, int(k), C.c_void_p(scores_ptr),
+                                          C.c_void_p(ids_ptr), N.MEM_HOST, None))
+
+    def debug_scores(self, q: torch.Tensor) -> torch.Tensor:
+        """Raw tensor-core scores [B, ntotal] (test hook for the tcgen05 path)."""
+        q = q.contiguous()
+        out = torch.empty((q.shape[0], self.ntotal), dtype=torch.float32, device=self.device)
+        N.check(N.load().vfi_index_debug_scores(self._h, C.c_void_p(q.data_ptr()), q.shape[0],
+                                                C.c_void_p(out.data_ptr()), N.MEM_DEVICE, _stream_ptr(self.device)))
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            N.load().vfi_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def merge_topk(scores: torch.Tensor, ids: torch.Tensor, k_out: int):
+    """scores float32 [G,B,k], ids int64 [G,B,k] on one GPU -> (ids [B,k_out], scores [B,k_out])."""
+    G, B, k_in = scores.shape
+    dev = scores.device
+    out_s = torch.empty((B, k_out), dtype=torch.float32, device=dev)
+    out_i = torch.empty((B, k_out), dtype=torch.int64, device=dev)
+    N.check(N.load().vfi_merge_topk(C.c_void_p(scores.contiguous().data_ptr()), C.c_void_p(ids.contiguous().data_ptr()),
+                                    G, B, k_in, int(k_out), C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()),
+                                    N.MEM_DEVICE, dev.index or 0, _stream_ptr(dev)))
+    return out_i, out_s
