@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py — the retrieval hot path on B200, one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c5|...] [--impl reference]
+
+Metric (BASELINE.json): queries/sec at 10M x 1024, top-100, 1024-query batch (config C3); the corpus
+is row-sharded over the N GPUs of the box (strong scaling: 10M rows in total for every N).
+A step = one pass of the hot path over one query batch: prepare queries -> fused tcgen05 GEMM+top-k'
+-> candidate reduction -> exact rescoring + certificate -> (N>1: NCCL all-gather + merge kernel).
+
+  value     whole-job queries/s with queries and corpus resident in HBM
+  e2e       the same through the reference-facing host call: pinned host queries in, host ids/scores
+            out, copies inside the timed region
+  roofline  the dominant kernel (dense_fused_kernel): algorithmic FLOPs 2*B*(N/G)*d per launch over its
+            CUDA-event duration, against MEASURED_PEAKS.json (sustained bf16)
+  cpu_baseline  the reference's CPU algorithm (oracle port of IndexFlatIP.search: blocked fp32 sgemm +
+            running top-k) on the host cores, on a bounded row slice, scaled linearly
+
+--impl reference runs only that CPU arm (rank 0) and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (total rows, dim, batch, k, store)
+    "c3": dict(n=10_000_000, d=1024, b=1024, k=100, desc="10Mx1024 bf16 corpus, 1024-query batch, top-100 (BASELINE configs[2])"),
+    "c2": dict(n=1_000_000, d=1024, b=256, k=100, desc="1Mx1024 bf16 corpus, 256-query batch, top-100 (BASELINE configs[1])"),
+    "c5": dict(n=50_000_000, d=768, b=1, k=10, desc="50Mx768 bf16 corpus, single query, top-10 (BASELINE configs[4])"),
+    "small": dict(n=200_000, d=1024, b=256, k=100, desc="200kx1024 smoke-size workload"),
+}
+SEED = 1234 + 2
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]),
+                    tf_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_arm(w, steps: int, warmup: int, rows_sample: int, threads: int | None):
+    """The reference's CPU retrieval path (IndexFlatIP.search restated: blocked fp32 sgemm + running top-k)
+    on the host cores, on a contiguous row slice of the same synthetic workload; q/s scaled to the full corpus."""
+    import numpy as np
+    import torch
+    from oracle import flat_ip
+    from veritasfi_b200 import synth
+
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rows = min(rows_sample, w["n"])
+    xb = synth.dense_corpus_np(rows, w["d"], SEED, dup_frac=0.0, bf16=True)
+    xq = synth.dense_queries_np(w["b"], w["d"], SEED, None, bf16=True)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        flat_ip.search_faiss_like(xq, xb, w["k"], threads=cores)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    t_step = sum(times) / len(times) * (w["n"] / rows)
+    return dict(value=w["b"] / t_step, unit="queries/s", cores=cores, kind="port",
+                sample=f"{rows} of {w['n']} rows x {w['b']} queries per step, time scaled x{w['n'] / rows:.1f}; "
+                       f"torch {torch.__version__} sgemm, {cores} threads"), t_step
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--cpu-rows", type=int, default=250_000, help="rows of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hint", type=int, default=1)
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    steps, warmup = max(1, args.steps), max(3, args.warmup) if args.impl == "b200" else max(0, args.warmup)
+    config = {"workload": f"{args.workload}: {w['desc']}", "corpus_rows": w["n"], "dim": w["d"], "batch": w["b"], "k": w["k"],
+              "sharding": f"row-sharded over {world} GPU(s)", "l2": "inputs exceed L2 (corpus shard >> 126 MB); no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cpu, t_step = cpu_reference_arm(w, min(steps, 3), min(warmup, 1), args.cpu_rows, None)
+        line = {"impl": "reference", "metric": "queries/sec", "value": cpu["value"], "unit": "queries/s", "n_gpus": args.gpus,
+                "steps": min(steps, 3), "warmup": min(warmup, 1), "ms_per_step": t_step * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": cpu,
+                "e2e": {"value": cpu["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from veritasfi_b200 import _native as N, synth
+    from veritasfi_b200.dense import DenseIndex
+    from veritasfi_b200.sharded import make_sharded_dense, shard_bounds
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    lo, hi = shard_bounds(w["n"], world, rank)
+    n_local = hi - lo
+    index = DenseIndex(w["d"], store="bf16", device=dev, id_offset=lo)
+    index.reserve(n_local)
+    chunk = 1 << 20
+    for r0 in range(0, n_local, chunk):   # corpus generated per shard, on the device, seed + global chunk id
+        r1 = min(n_local, r0 + chunk)
+        index.add(synth.dense_corpus_torch(r1 - r0, w["d"], SEED + 1000 * rank + (r0 // chunk), dev))
+    torch.cuda.synchronize()
+    index.set_option(N.OPT_TAU_HINT, args.hint)
+    index.set_option(N.OPT_PROFILE, 1)
+    searcher = make_sharded_dense(index)
+    q_dev = synth.dense_queries_torch(w["b"], w["d"], SEED, dev)
+    q_pin = torch.empty((w["b"], w["d"]), dtype=torch.float32).pin_memory()
+    q_pin.copy_(q_dev.cpu())
+    out_i_pin = torch.empty((w["b"], w["k"]), dtype=torch.int64).pin_memory()
+    out_s_pin = torch.empty((w["b"], w["k"]), dtype=torch.float32).pin_memory()
+
+    def step_device():
+        return searcher.search(q_dev, w["k"])
+
+    def step_e2e():
+        if world == 1:   # the reference-facing host call of the C ABI: H2D, search, D2H inside
+            index.search_host_into(q_pin.data_ptr(), w["b"], w["k"], out_s_pin.data_ptr(), out_i_pin.data_ptr())
+        else:
+            qd = q_pin.to(dev, non_blocking=True)
+            ids, scores = searcher.search(qd, w["k"])
+            out_i_pin.copy_(ids, non_blocking=True)
+            out_s_pin.copy_(scores, non_blocking=True)
+            torch.cuda.synchronize()
+
+    def timed(fn, k_steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(k_steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        # host-synchronous steps (e2e) are bounded below by wall time; use the larger of the two clocks
+        ms = max(ms, wall * 1e3) if fn is step_e2e else ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(warmup):
+        step_device()
+    for _ in range(min(warmup, 3)):
+        step_e2e()
+    index.stats(reset=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = N.launch_count()
+    ms_total = timed(step_device, steps)
+    launches = N.launch_count() - launches0
+    st = index.stats()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, steps)
+    ids, scores = step_device()
+    torch.cuda.synchronize()
+
+    kernel_ms = st.fused_ms_total / max(1, st.fused_ms_samples)
+    kt = torch.tensor([kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+    kernel_ms = float(kt.item())
+
+    if rank == 0:
+        peaks = read_peaks()
+        ms_step = ms_total / steps
+        flops_per_launch = 2.0 * w["b"] * n_local * w["d"]
+        achieved_tf = flops_per_launch / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else 0.0
+        tensor_bound = w["b"] >= 128
+        if tensor_bound:
+            roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                        "frac": achieved_tf / peaks["tf_sustained"], "traffic": None,
+                        "kernel": "dense_fused_kernel<MODE_TOPK>", "kernel_ms": kernel_ms,
+                        "peak_source": f"{peaks['source']} MEASURED_PEAKS.json bf16_tflops_sustained",
+                        "algorithmic": f"2*B*(N/G)*d = {flops_per_launch:.4g} FLOP per launch"}
+        else:
+            bytes_per_launch = float(n_local) * w["d"] * 2
+            gbs = bytes_per_launch / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+            roofline = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                        "traffic": None, "kernel": "gemv_topk_kernel", "kernel_ms": kernel_ms,
+                        "peak_source": f"{peaks['source']} MEASURED_PEAKS.json hbm_gbs",
+                        "algorithmic": f"(N/G)*d*2 = {bytes_per_launch:.4g} B per launch"}
+        line = {"metric": "queries/sec", "value": w["b"] / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": steps,
+                "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic", "config": config, "roofline": roofline, "clocks": clocks,
+                "e2e": {"value": w["b"] / (ms_e2e / steps * 1e-3), "unit": "queries/s", "ms_per_step": ms_e2e / steps,
+                        "h2d_bytes_per_step": w["b"] * w["d"] * 4, "d2h_bytes_per_step": w["b"] * w["k"] * 12},
+                "gpu_launches": int(launches),
+                "search": {"path": int(st.last_path), "overfetch": int(st.last_overfetch), "retried_queries": int(st.retried_queries),
+                           "hint_retries": int(st.hint_retries), "max_abs_tc_err": float(st.max_abs_err)}}
+        if not args.no_cpu_baseline and world == 1:
+            cpu, _ = cpu_reference_arm(w, 2, 1, args.cpu_rows, None)
+            line["cpu_baseline"] = cpu
+        elif world > 1:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

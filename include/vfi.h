@@ -96,7 +96,7 @@ enum {
   VFI_OPT_OVERFETCH = 1,     /* candidates kept per query by the tensor-core pass (0 = auto) */
   VFI_OPT_FORCE_PATH = 2,    /* 0 auto, 1 exhaustive exact, 2 fused tcgen05, 3 streaming GEMV */
   VFI_OPT_PROFILE = 3,       /* 1: bracket the dominant kernel with CUDA events */
-  VFI_OPT_TAU_HINT = 4,      /* 1: estimate a per-query admission threshold from a row sample */
+  VFI_OPT_TAU_HINT = 4,      /* 1: estimate a per-query admission threshold from a row sample (2: debug, admit nothing) */
   VFI_OPT_NUM_CTAS = 5       /* 0 = one CTA per SM */
 };
 int vfi_index_set_option(vfi_index_t* idx, int opt, int64_t value);
@@ -112,6 +112,7 @@ typedef struct vfi_search_stats {
   int last_overfetch;          /* k' used by the last search */
   float last_eps;              /* largest certificate epsilon of the last search */
   float max_abs_err;           /* max |tensor-core score - exact score| over rescored candidates */
+  int64_t hint_retries;        /* batches redone without the admission hint */
 } vfi_search_stats;
 int vfi_index_get_stats(vfi_index_t* idx, vfi_search_stats* out, int reset);
 

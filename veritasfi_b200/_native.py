@@ -31,6 +31,7 @@ class SearchStats(C.Structure):
         ("searches", C.c_int64), ("queries", C.c_int64), ("retried_queries", C.c_int64),
         ("fused_launches", C.c_int64), ("fused_ms_total", C.c_double), ("fused_ms_samples", C.c_int64),
         ("last_path", C.c_int), ("last_overfetch", C.c_int), ("last_eps", C.c_float), ("max_abs_err", C.c_float),
+        ("hint_retries", C.c_int64),
     ]
 
 

@@ -190,6 +190,29 @@ __global__ void __launch_bounds__(256) cand_reduce_kernel(const uint64_t* __rest
   }
 }
 
+// tau[q] = the m-th best score among the sampled rows' raw tensor-core scores (one CTA per query)
+struct ScoreRowSrc {
+  const float* s;
+  int n;
+  template <class F>
+  __device__ void for_each(F f) const {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) f(make_key(s[i], static_cast<uint32_t>(i)));
+  }
+};
+__global__ void __launch_bounds__(256) tau_from_scores_kernel(const float* __restrict__ scores, int64_t ld, int n_valid,
+                                                              int m, float* __restrict__ tau, int debug_inf) {
+  extern __shared__ uint8_t smem_raw[];
+  SelectSmem* sm = reinterpret_cast<SelectSmem*>(smem_raw);
+  const int q = blockIdx.x;
+  ScoreRowSrc src{scores + static_cast<int64_t>(q) * ld, n_valid};
+  const uint32_t n = block_topk(src, static_cast<uint32_t>(n_valid), static_cast<uint32_t>(m), sm);
+  if (threadIdx.x == 0) {
+    float t = (n >= static_cast<uint32_t>(m)) ? key_score(sm->keys[m - 1]) : -INFINITY;
+    if (debug_inf) t = INFINITY;
+    tau[q] = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // K2a: canonical scores.  One warp = 32 (query, row) pairs of the same query, lane = row.
 // The 32 rows are staged through shared memory in 64-element chunks with coalesced 16-byte

@@ -443,23 +443,26 @@ int exhaustive_pass(vfi_index* idx, const int* qsel_dev, int nsel, int k, float*
   return VFI_OK;
 }
 
+// n_rows/row_stride: the corpus view scanned — (idx->n, 1) for the full shard, (R, s) for a strided row sample
 int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, int64_t ld_scores, const float* tau,
-                 int* o_groups, int* o_nq_pad, int* o_cap, cudaStream_t st) {
+                 int* o_groups, int* o_nq_pad, int* o_cap, cudaStream_t st, int64_t n_rows = -1, int64_t row_stride = 1,
+                 bool profile = true) {
+  if (n_rows < 0) n_rows = idx->n;
   const int n_mtiles = static_cast<int>(ceil_div(nq, vfi::kBM));
   int n_ctas = idx->opt_num_ctas > 0 ? static_cast<int>(idx->opt_num_ctas) : idx->num_sms;
   n_ctas = std::max(n_ctas, n_mtiles);
-  const int n_tiles = static_cast<int>(ceil_div(idx->n, vfi::kBN));
+  const int n_tiles = static_cast<int>(ceil_div(n_rows, vfi::kBN));
   int n_groups = std::max(1, n_ctas / n_mtiles);
   n_groups = std::min(n_groups, std::max(1, n_tiles));
   const int nq_pad = n_mtiles * vfi::kBM;
   const int cap = 2 * keep + 32;
   CUtensorMap tq, td;
   VFI_TRY(make_tmap(&tq, idx->w_qg.p, nq, idx->kp, idx->kp, vfi::kBM));
-  VFI_TRY(make_tmap(&td, idx->g, idx->n, idx->kp, idx->kp, vfi::kBN));
+  VFI_TRY(make_tmap(&td, idx->g, n_rows, idx->kp, idx->kp * row_stride, vfi::kBN));
   vfi::DenseParams p{};
   p.nq = nq;
   p.nq_pad = nq_pad;
-  p.n_rows = static_cast<int>(idx->n);
+  p.n_rows = static_cast<int>(n_rows);
   p.n_kblocks = static_cast<int>(idx->kp / vfi::kBK);
   p.n_mtiles = n_mtiles;
   p.n_groups = n_groups;
@@ -475,7 +478,7 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
     p.cand = idx->w_cand.as<uint64_t>();
     p.cand_count = idx->w_cand_count.as<uint32_t>();
   }
-  const bool prof = idx->opt_profile != 0;
+  const bool prof = idx->opt_profile != 0 && profile;
   if (prof) cudaEventRecord(idx->ev0, st);
   const int grid = n_groups * n_mtiles;
   if (mode == vfi::MODE_TOPK)
@@ -485,7 +488,7 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
   LAUNCHED();
   if (prof) cudaEventRecord(idx->ev1, st);
   VFI_CUDA(cudaGetLastError());
-  idx->stats.fused_launches++;
+  if (profile) idx->stats.fused_launches++;
   if (o_groups) *o_groups = n_groups;
   if (o_nq_pad) *o_nq_pad = nq_pad;
   if (o_cap) *o_cap = cap;
@@ -493,7 +496,8 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
 }
 
 // one batch of <= kMaxQueriesPerLaunch queries already on the device; results to device buffers
-int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t st,
+                 bool no_hint = false) {
   VFI_TRY(prep_queries(idx, q_dev, nq, st));
   const int64_t n = idx->n;
   int keep = idx->opt_overfetch > 0 ? static_cast<int>(idx->opt_overfetch)
@@ -514,6 +518,29 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
 
   int n_groups = 0, nq_pad = 0, cap = 0;
   const float* tau = nullptr;
+  if (path == 2 && idx->opt_tau_hint != 0 && !no_hint) {
+    // admission hint: the m-th best score of a strided row sample estimates a threshold that about
+    // 4k' rows of the shard exceed.  It only prunes work; exactness is re-established below.
+    // Sample every s-th row with s = 2k'+1.  tau = the m-th best sampled score with m = 8: about
+    // m*s = 16k' rows of the shard are expected above it, and fewer than k' with probability
+    // P(Gamma(8) < 1/2) ~ 1e-7 per query (then the batch is simply redone without the hint).
+    const int m = 8;
+    const int64_t rs = 2 * static_cast<int64_t>(keep) + 1;
+    const int64_t rr = n / rs;
+    if (rr >= 64 * m || idx->opt_tau_hint == 2) {
+      const int64_t ld = ceil_div(rr, vfi::kBN) * vfi::kBN;
+      const int64_t nq_pad_s = ceil_div(nq, vfi::kBM) * vfi::kBM;
+      VFI_TRY(idx->w_dbg.ensure(static_cast<size_t>(nq_pad_s) * ld * 4));
+      VFI_TRY(idx->w_tau.ensure(static_cast<size_t>(nq) * 4));
+      VFI_TRY(launch_fused(idx, nq, 32, vfi::MODE_STORE, idx->w_dbg.as<float>(), ld, nullptr, nullptr, nullptr, nullptr, st, rr,
+                           rs, false));
+      vfi::tau_from_scores_kernel<<<nq, 256, sizeof(vfi::SelectSmem), st>>>(idx->w_dbg.as<float>(), ld, static_cast<int>(rr), m,
+                                                                           idx->w_tau.as<float>(), idx->opt_tau_hint == 2 ? 1 : 0);
+      LAUNCHED();
+      VFI_CUDA(cudaGetLastError());
+      tau = idx->w_tau.as<float>();
+    }
+  }
   if (path == 2) {
     VFI_TRY(launch_fused(idx, nq, keep, vfi::MODE_TOPK, nullptr, 0, tau, &n_groups, &nq_pad, &cap, st));
   } else {
@@ -590,6 +617,11 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
     }
   }
   const int n_flagged = idx->h_flag[0];
+  if (n_flagged > 0 && tau != nullptr && idx->opt_tau_hint == 1) {
+    // the hint pruned too much for some query: redo the batch without it (same kernels, no pruning)
+    idx->stats.hint_retries++;
+    return search_batch(idx, q_dev, nq, k, out_scores, out_ids, st, true);
+  }
   if (n_flagged > 0) {
     idx->stats.retried_queries += n_flagged;
     VFI_TRY(exhaustive_pass(idx, d_flag + 1, n_flagged, k, out_scores, out_ids, st));
