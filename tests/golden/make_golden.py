@@ -1,0 +1,55 @@
+"""Generate tests/golden/ensemble_golden.json by running the UNMODIFIED reference classes
+(/root/reference/src/utils/{faissRetriever,bm25Retriever,ensembleRetriever}.py) over tests/fixture_world.py.
+
+The reference's third-party dependencies are absent from this image (faiss, bm25s, PyStemmer, langchain_*),
+so they are replaced by shims: `faiss` and the scoring half of `bm25s` are backed by the CPU ORACLE (oracle/),
+tokenisation by the host tokenizer of veritasfi_b200.bm25_compat, PyStemmer by an identity stemmer.  What the
+fixture pins is therefore the reference's own orchestration — depth-2048 dense search, shared seen_ids
+de-duplication, bundle gathering, prev/next expansion at 0.72/0.66, title-summary mapping, BM25 k = N then
+slice — on top of the canonical arithmetic.  Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+import tempfile
+
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import fixture_world as fw  # noqa: E402
+
+REFERENCE = "/root/reference"
+
+
+from oracle_doubles import IdentityStemmer, install_reference_shims, write_bm25_dir  # noqa: E402
+
+
+def main():
+    install_reference_shims()
+    sys.path.insert(0, REFERENCE)
+    from src.utils.ensembleRetriever import EnsembleRetriever  # the reference, unmodified
+
+    world = fw.make_world()
+    out = {"n_chunks": len(world["metas"]), "cases": []}
+    with tempfile.TemporaryDirectory() as tmp:
+        write_bm25_dir(world, tmp)
+        for cfg in [dict(k=5, enable_expand=True), dict(k=3, faiss_k=6, bm25_k=4, faiss_ts_k=2, enable_expand=False),
+                    dict(k=4, faiss_k=0, bm25_k=5, faiss_ts_k=3, enable_expand=True)]:
+            chroma, ts = fw.make_collections(world)
+            r = EnsembleRetriever(tmp, chroma, ts, cfg["k"], fw.FakeEmbeddings(world),
+                                  **{a: b for a, b in cfg.items() if a != "k"})
+            for qi, (q, hyde) in enumerate(fw.QUERIES):
+                chunks = r.invoke(q, list(hyde))
+                out["cases"].append({"cfg": cfg, "query": qi, "chunks": fw.summarize(chunks)})
+    with open(os.path.join(HERE, "ensemble_golden.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", len(out["cases"]), "cases;", sum(len(c["chunks"]) for c in out["cases"]), "chunks")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,124 @@
+"""Boundary tests (BASELINE config C1): the reference's own call sites drive this repo.
+
+  * golden fixture  tests/golden/ensemble_golden.json was produced by the UNMODIFIED reference
+                    EnsembleRetriever/FaissRetriever/BM25Retriever (make_golden.py);
+  * CPU             the host-side mirror (veritasfi_b200.retrievers) reproduces it with oracle doubles injected
+                    where the CUDA library would be called — this checks the orchestration logic only;
+  * GPU             the mirror on the real kernels reproduces it, and so do the unmodified reference files once
+                    veritasfi_b200.dropin.install() has put our faiss/bm25s modules in place (build container only:
+                    /root/reference does not exist on the GPU box)."""
+import json
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import fixture_world as fw  # noqa: E402
+import oracle_doubles as od  # noqa: E402
+
+REFERENCE = "/root/reference"
+CONFIGS = [dict(k=5, enable_expand=True), dict(k=3, faiss_k=6, bm25_k=4, faiss_ts_k=2, enable_expand=False),
+           dict(k=4, faiss_k=0, bm25_k=5, faiss_ts_k=3, enable_expand=True)]
+
+
+def _run(cls, tmp, world):
+    cases = []
+    for cfg in CONFIGS:
+        chroma, ts = fw.make_collections(world)
+        r = cls(tmp, chroma, ts, cfg["k"], fw.FakeEmbeddings(world), **{a: b for a, b in cfg.items() if a != "k"})
+        for qi, (q, hyde) in enumerate(fw.QUERIES):
+            cases.append({"cfg": cfg, "query": qi, "chunks": fw.summarize(r.invoke(q, list(hyde)))})
+    return cases
+
+
+def _assert_equal_to_golden(cases):
+    gold = fw.load_golden()["cases"]
+    assert len(cases) == len(gold)
+    for got, want in zip(cases, gold):
+        assert got["cfg"] == want["cfg"] and got["query"] == want["query"]
+        assert got["chunks"] == want["chunks"], f"cfg={got['cfg']} query={got['query']}"
+
+
+def test_golden_covers_every_retriever_tag_bundles_and_expansion():
+    gold = fw.load_golden()
+    tags = {c[0] for case in gold["cases"] for c in case["chunks"]}
+    assert tags == {"FAISS", "Title Summary", "BM25"}
+    world = fw.make_world()
+    assert gold["n_chunks"] == len(world["metas"])
+    # some FAISS hit brought more chunks than it retrieved directly (bundle or neighbour expansion)
+    assert any(sum(1 for c in case["chunks"] if c[0] == "FAISS") > (case["cfg"].get("faiss_k", case["cfg"]["k"]) * (1 + len(fw.QUERIES[case["query"]][1])))
+               for case in gold["cases"] if case["cfg"].get("faiss_k", 1) != 0)
+
+
+def test_mirror_with_oracle_doubles_reproduces_the_reference(tmp_path, monkeypatch):
+    from veritasfi_b200 import retrievers
+    world = fw.make_world()
+    od.write_bm25_dir(world, str(tmp_path))
+    monkeypatch.setattr(retrievers.faiss_compat, "IndexFlatIP", od.OracleIndexFlatIP)
+    monkeypatch.setattr(retrievers.faiss_compat, "normalize_L2", od.oracle_normalize_L2)
+    monkeypatch.setattr(retrievers.bm25_compat, "BM25", od.OracleBM25)
+    monkeypatch.setattr(retrievers, "make_stemmer", lambda lang="english": od.IdentityStemmer())
+    _assert_equal_to_golden(_run(retrievers.EnsembleRetriever, str(tmp_path), world))
+
+
+def test_mirror_replaces_metadata_scans_with_maps_but_keeps_fetch_pattern(tmp_path, monkeypatch):
+    from veritasfi_b200 import retrievers
+    world = fw.make_world()
+    od.write_bm25_dir(world, str(tmp_path))
+    monkeypatch.setattr(retrievers.faiss_compat, "IndexFlatIP", od.OracleIndexFlatIP)
+    monkeypatch.setattr(retrievers.faiss_compat, "normalize_L2", od.oracle_normalize_L2)
+    monkeypatch.setattr(retrievers.bm25_compat, "BM25", od.OracleBM25)
+    chroma, ts = fw.make_collections(world)
+    r = retrievers.EnsembleRetriever(str(tmp_path), chroma, ts, 5, fw.FakeEmbeddings(world), enable_expand=True)
+    before = chroma.get_calls
+    out = r.invoke(*[fw.QUERIES[1][0], list(fw.QUERIES[1][1])])
+    bundles = len({c["bundle_id"] for c in out})
+    assert chroma.get_calls - before == bundles          # one Chroma fetch per emitted bundle, like the reference
+    with pytest.raises(NotImplementedError):
+        r.bm25_retriever.invoke("x", 3, metadata_filters={"a": 1})
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference tree only exists in the build container")
+def test_committed_golden_is_what_the_unmodified_reference_produces(tmp_path):
+    for name in [m for m in sys.modules if m == "src" or m.startswith("src.")]:
+        del sys.modules[name]
+    od.install_reference_shims()
+    sys.path.insert(0, REFERENCE)
+    try:
+        from src.utils.ensembleRetriever import EnsembleRetriever
+        world = fw.make_world()
+        od.write_bm25_dir(world, str(tmp_path))
+        _assert_equal_to_golden(_run(EnsembleRetriever, str(tmp_path), world))
+    finally:
+        sys.path.remove(REFERENCE)
+        for name in ("faiss", "bm25s", "Stemmer", "langchain_huggingface", "langchain_community", "langchain_community.vectorstores",
+                     "langchain_chroma", "langchain_core", "langchain_core.documents"):
+            sys.modules.pop(name, None)
+        for name in [m for m in sys.modules if m == "src" or m.startswith("src.")]:
+            del sys.modules[name]
+
+
+@pytest.mark.gpu
+def test_mirror_on_the_gpu_kernels_reproduces_the_reference(tmp_path):
+    from veritasfi_b200 import retrievers
+    world = fw.make_world()
+    od.write_bm25_dir(world, str(tmp_path))
+    _assert_equal_to_golden(_run(retrievers.EnsembleRetriever, str(tmp_path), world))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference tree only exists in the build container")
+def test_unmodified_reference_files_on_the_gpu_kernels(tmp_path):
+    from veritasfi_b200 import dropin
+    od.install_reference_shims()      # langchain_* stubs
+    dropin.install(override_stemmer=True)   # faiss / bm25s / Stemmer -> this package
+    sys.path.insert(0, REFERENCE)
+    try:
+        from src.utils.ensembleRetriever import EnsembleRetriever
+        world = fw.make_world()
+        od.write_bm25_dir(world, str(tmp_path))
+        _assert_equal_to_golden(_run(EnsembleRetriever, str(tmp_path), world))
+    finally:
+        sys.path.remove(REFERENCE)
+        dropin.uninstall()

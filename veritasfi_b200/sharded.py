@@ -54,9 +54,9 @@ class ShardedSearcher:
         if self.world == 1:
             return ids, scores
         mine = pack(scores, ids)
-        gathered = torch.empty((self.world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
-        dist.all_gather_into_tensor(gathered, mine, group=self.group)
-        g_scores, g_ids = unpack(gathered, k)
+        flat = torch.empty((self.world * mine.shape[0], mine.shape[1]), dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(flat, mine, group=self.group)     # rank-major concatenation along dim 0
+        g_scores, g_ids = unpack(flat.view(self.world, mine.shape[0], mine.shape[1]), k)
         return self.merge(g_scores, g_ids, k)
 
 
