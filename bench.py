@@ -223,6 +223,29 @@ def main():
         step_device()
     for _ in range(min(warmup, 3)):
         step_e2e()
+    if os.environ.get("VFI_BENCH_BREAKDOWN"):
+        from veritasfi_b200 import sharded as sh
+        from veritasfi_b200.dense import merge_topk
+
+        def tick(label, fn, acc):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = fn()
+            torch.cuda.synchronize()
+            acc[label] = acc.get(label, 0.0) + (time.perf_counter() - t0) * 1e3
+            return r
+        acc = {}
+        for _ in range(5):
+            ids_l, sc_l = tick("local_search", lambda: index.search_batch(q_dev, w["k"]), acc)
+            if world > 1:
+                mine = tick("pack", lambda: sh.pack(sc_l, ids_l), acc)
+                flat = torch.empty((world * mine.shape[0], mine.shape[1]), dtype=mine.dtype, device=dev)
+                tick("all_gather", lambda: dist.all_gather_into_tensor(flat, mine), acc)
+                gs, gi = tick("unpack", lambda: sh.unpack(flat.view(world, mine.shape[0], mine.shape[1]), w["k"]), acc)
+                tick("merge", lambda: merge_topk(gs, gi, w["k"]), acc)
+            tick("h2d_queries", lambda: q_pin.to(dev, non_blocking=True), acc)
+            tick("d2h_results", lambda: (out_i_pin.copy_(ids_l, non_blocking=True), out_s_pin.copy_(sc_l, non_blocking=True)), acc)
+        print(f"[breakdown rank {rank}] " + "  ".join(f"{k}={v / 5:.3f}ms" for k, v in acc.items()), file=sys.stderr, flush=True)
     index.stats(reset=True)
     sampler = ClockSampler(local_rank)
     if rank == 0:

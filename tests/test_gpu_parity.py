@@ -117,6 +117,8 @@ def test_ties_duplicates_zero_rows_and_padding(torch_cuda):
     xq = rng.integers(-2, 3, size=(140, d)).astype(np.float32)
     xq[0] = xb[17]
     xq[1] = 0                                                      # zero query: every score ties at 0
+    xb[200, 3] = np.float32(1e-39)                                 # an fp32 denormal (a bf16 denormal after rounding)
+    xb[201, 5] = np.float32(-3e-40)
     for path in (1, 2, 3):
         idx = DenseIndex(d, store="bf16")
         idx.add(xb)

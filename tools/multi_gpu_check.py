@@ -1,0 +1,54 @@
+"""Multi-GPU parity check, launched one process per GPU:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P tools/multi_gpu_check.py
+Every rank holds a row shard of one seeded corpus; the NCCL all-gather + merge kernel result must equal the
+unsharded CPU oracle bit for bit."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import flat_ip  # noqa: E402
+from veritasfi_b200 import _native as N, synth  # noqa: E402
+from veritasfi_b200.dense import DenseIndex  # noqa: E402
+from veritasfi_b200.sharded import make_sharded_dense, shard_bounds  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+    for (n, d, nq, k, path) in [(120_001, 256, 200, 100, N.PATH_FUSED), (50_000, 768, 1, 10, N.PATH_GEMV), (3_000, 64, 9, 20, 0)]:
+        xb = synth.dense_corpus_np(n, d, 99)
+        xb[n - 1] = xb[7]                      # duplicate on the last shard: cross-shard tie
+        xq = synth.dense_queries_np(nq, d, 99, xb)
+        xq[0] = xb[7]
+        lo, hi = shard_bounds(n, world, rank)
+        idx = DenseIndex(d, store="bf16", device=dev, id_offset=lo)
+        idx.add(xb[lo:hi])
+        idx.set_option(N.OPT_FORCE_PATH, path)
+        idx.set_option(N.OPT_TAU_HINT, 1)
+        searcher = make_sharded_dense(idx)
+        ids, scores = searcher.search(torch.from_numpy(xq).to(dev), k)
+        torch.cuda.synchronize()
+        D0, I0 = flat_ip.search(xq, xb, k)
+        good = bool((ids.cpu().numpy() == I0).all() and (scores.cpu().numpy() == D0).all())
+        flag = torch.tensor([1 if good else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"[multi-gpu G={world} n={n} d={d} nq={nq} k={k}] all ranks equal to unsharded oracle: {bool(flag.item())}", flush=True)
+        ok &= bool(flag.item())
+        idx.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

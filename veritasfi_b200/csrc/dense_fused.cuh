@@ -34,10 +34,10 @@ constexpr int kBK = 64;
 constexpr int kStages = 4;
 constexpr int kABytes = kBM * kBK * 2;   // 16 KB
 constexpr int kBBytes = kBN * kBK * 2;   // 32 KB
-constexpr int kDenseThreads = 256;       // warps 0-3: TMA / MMA / TMEM-alloc / spare, 4-7: epilogue
+constexpr int kDenseThreads = 384;       // warps 0-3: TMA / MMA / TMEM-alloc / spare, 4-7 and 8-11: two epilogue sets
 constexpr int kTmemCols = 512;
 constexpr int kDenseSmemBytes =
-    1024 /*align slack*/ + kStages * (kABytes + kBBytes) + 256 /*barriers*/ + 4 * 256 * 4 /*hist*/;
+    1024 /*align slack*/ + kStages * (kABytes + kBBytes) + 256 /*barriers*/ + 8 * 256 * 4 /*hist*/;
 
 enum { MODE_TOPK = 0, MODE_STORE = 1 };
 
@@ -51,8 +51,8 @@ struct DenseParams {
   int n_tiles;            // ceil(n_rows / 256)
   int keep;               // k'
   int cap;                // keys per (group, query) buffer; cap >= keep + 64
-  uint64_t* cand;         // [n_groups][nq_pad][cap]
-  uint32_t* cand_count;   // [n_groups][nq_pad]
+  uint64_t* cand;         // [2*n_groups][nq_pad][cap]   (one buffer per epilogue set)
+  uint32_t* cand_count;   // [2*n_groups][nq_pad]
   const float* tau_init;  // [nq] admission hints (rows with score <= hint are ignored) or nullptr
   float* scores_out;      // MODE_STORE: [nq_pad][ld_scores]
   int64_t ld_scores;
@@ -150,25 +150,34 @@ dense_fused_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
   } else if (active && warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> threshold filter =====================
-    const uint32_t wq = warp - 4;                 // TMEM lane quadrant of this warp
+    // Two warp sets: set 0 (warps 4-7) drains accumulator stage 0 = the even tiles of this CTA, set 1
+    // (warps 8-11) stage 1 = the odd tiles, so two tiles are filtered concurrently.  Each set keeps its
+    // own threshold and key buffer per query.
+    const uint32_t set = (warp - 4) >> 2;
+    const uint32_t wq = (warp - 4) & 3;            // TMEM lane quadrant of this warp (= warp % 4)
     const int qi = m_tile * kBM + wq * 32 + lane;  // the query this thread owns
     const bool valid_q = qi < p.nq;
-    uint32_t* my_hist = hist + wq * 256;
+    uint32_t* my_hist = hist + (warp - 4) * 256;
 
     uint64_t* buf = nullptr;
     uint32_t count = 0;
     uint64_t tau_key = kKeyNone;
     float tau_f = -INFINITY;
+    const size_t slot = (static_cast<size_t>(group) * 2 + set) * p.nq_pad + qi;
     if (MODE == MODE_TOPK) {
-      buf = p.cand + (static_cast<size_t>(group) * p.nq_pad + qi) * p.cap;
+      buf = p.cand + slot * p.cap;
       if (valid_q && p.tau_init != nullptr) {
         tau_f = p.tau_init[qi];
         tau_key = make_key(tau_f, 0u);   // admits score > hint only
       }
     }
-    uint32_t acc = 0, acc_phase = 0;
-    for (int t = group; t < p.n_tiles; t += p.n_groups) {
+    const uint32_t acc = set;
+    uint32_t acc_phase = 0;
+    int local_tile = 0;
+    for (int t = group; t < p.n_tiles; t += p.n_groups, ++local_tile) {
+      if ((local_tile & 1) != static_cast<int>(set)) continue;
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      acc_phase ^= 1;
       ptx::tc_fence_after();
       const uint32_t row0 = static_cast<uint32_t>(t) * kBN;
       const uint32_t taddr = tmem_base + ((wq * 32u) << 16) + acc * kBN;
@@ -186,16 +195,25 @@ dense_fused_kernel(const __grid_constant__ CUtensorMap tmap_q,
               dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
         } else {
-          float mx = v[0];
+          // group maxima (4 columns each) feed both the chunk test and the per-group tests
+          float m4[8];
 #pragma unroll
-          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+          for (int g = 0; g < 8; ++g)
+            m4[g] = fmaxf(fmaxf(v[4 * g], v[4 * g + 1]), fmaxf(v[4 * g + 2], v[4 * g + 3]));
+          const float mx = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])),
+                                 fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
           if (valid_q && mx >= tau_f) {
             const uint32_t id0 = row0 + c * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (v[j] >= tau_f && id0 + j < static_cast<uint32_t>(p.n_rows)) {
-                const uint64_t key = make_key(v[j], id0 + j);
-                if (key > tau_key) buf[count++] = key;
+            for (int g = 0; g < 8; ++g) {
+              if (m4[g] >= tau_f) {
+#pragma unroll
+                for (int j = 4 * g; j < 4 * g + 4; ++j) {
+                  if (v[j] >= tau_f && id0 + j < static_cast<uint32_t>(p.n_rows)) {
+                    const uint64_t key = make_key(v[j], id0 + j);
+                    if (key > tau_key) buf[count++] = key;
+                  }
+                }
               }
             }
           }
@@ -221,11 +239,9 @@ dense_fused_kernel(const __grid_constant__ CUtensorMap tmap_q,
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
     if (MODE == MODE_TOPK) {
-      p.cand_count[static_cast<size_t>(group) * p.nq_pad + qi] = valid_q ? count : 0u;
+      p.cand_count[slot] = valid_q ? count : 0u;
     }
   }
 

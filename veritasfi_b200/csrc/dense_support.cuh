@@ -24,6 +24,19 @@ __device__ __forceinline__ float bf16_to_f32(uint16_t h) {
   return __uint_as_float(static_cast<uint32_t>(h) << 16);
 }
 
+// fp32 bit pattern -> the same value as fp64 with integer ops only (fp64 conversions share the slow
+// fp64 pipe with the DFMA chain).  Normal numbers: sign | (exponent + 896) << 52 | mantissa << 29;
+// zero maps to zero.  Denormals / inf / NaN are not representable this way: `odd` collects a flag and
+// the caller redoes the batch with the conversion instruction (never taken on real embeddings).
+__device__ __forceinline__ double widen_f32_bits(uint32_t f, uint32_t& odd) {
+  const uint32_t e = f & 0x7F800000u;
+  const uint32_t hi_n = (f & 0x80000000u) | (((f & 0x7FFFFFFFu) >> 3) + 0x38000000u);
+  const uint32_t hi = (e != 0u) ? hi_n : (f & 0x80000000u);
+  const uint32_t lo = (e != 0u) ? (f << 29) : 0u;
+  odd |= (e == 0x7F800000u) | ((e == 0u) & ((f & 0x007FFFFFu) != 0u));
+  return __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
+}
+
 // butterfly (xor 16,8,4,2,1) sum in fp64 — the fixed order the oracle restates for norms
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
@@ -145,15 +158,19 @@ __global__ void normalize_l2_kernel(float* __restrict__ x, int64_t n, int d) {
 // ------------------------------------------------------------------------------------------
 struct GroupBufSrc {
   const uint64_t* cand;
-  const uint32_t* cnt;
+  const uint32_t* pref;   // shared memory: exclusive prefix of the per-group counts, [n_groups + 1]
   int n_groups, nq_pad, cap, q;
   template <class F>
   __device__ void for_each(F f) const {
-    for (int g = 0; g < n_groups; ++g) {
-      const size_t slot = static_cast<size_t>(g) * nq_pad + q;
-      const uint32_t c = min(cnt[slot], static_cast<uint32_t>(cap));
-      const uint64_t* b = cand + slot * cap;
-      for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) f(b[i]);
+    // flat index -> (group, offset) by binary search in the prefix array: every load is independent
+    const uint32_t total = pref[n_groups];
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+      int lo = 0, hi = n_groups;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (pref[mid] <= i) lo = mid; else hi = mid;
+      }
+      f(cand[(static_cast<size_t>(lo) * nq_pad + q) * cap + (i - pref[lo])]);
     }
   }
 };
@@ -168,16 +185,29 @@ __global__ void __launch_bounds__(256) cand_reduce_kernel(const uint64_t* __rest
   extern __shared__ uint8_t smem_raw[];
   SelectSmem* sm = reinterpret_cast<SelectSmem*>(smem_raw);
   const int q = blockIdx.x;
-  __shared__ uint32_t s_total;
-  if (threadIdx.x == 0) s_total = 0;
-  __syncthreads();
-  uint32_t part = 0;
+  __shared__ uint32_t s_pref[1025];
+  // counts of all group buffers in one coalesced sweep, then an exclusive scan (n_groups <= 1024)
   for (int g = threadIdx.x; g < n_groups; g += blockDim.x)
-    part += min(cnt[static_cast<size_t>(g) * nq_pad + q], static_cast<uint32_t>(cap));
-  if (part) atomicAdd(&s_total, part);
+    s_pref[g + 1] = min(cnt[static_cast<size_t>(g) * nq_pad + q], static_cast<uint32_t>(cap));
+  if (threadIdx.x == 0) s_pref[0] = 0;
   __syncthreads();
-  const uint32_t total = s_total;
-  GroupBufSrc src{cand, cnt, n_groups, nq_pad, cap, q};
+  if (threadIdx.x < 32) {
+    uint32_t carry = 0;
+    for (int base = 0; base < n_groups; base += 32) {
+      const int g = base + threadIdx.x;
+      uint32_t v = (g < n_groups) ? s_pref[g + 1] : 0u;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (static_cast<int>(threadIdx.x) >= o) v += t;
+      }
+      if (g < n_groups) s_pref[g + 1] = v + carry;
+      carry += __shfl_sync(0xFFFFFFFFu, v, 31);
+    }
+  }
+  __syncthreads();
+  const uint32_t total = s_pref[n_groups];
+  GroupBufSrc src{cand, s_pref, n_groups, nq_pad, cap, q};
   const uint32_t n = block_topk(src, total, static_cast<uint32_t>(keep), sm);
   for (uint32_t i = threadIdx.x; i < static_cast<uint32_t>(keep); i += blockDim.x)
     out_keys[static_cast<size_t>(q) * keep + i] = (i < n) ? sm->keys[i] : kKeyNone;
@@ -196,7 +226,17 @@ struct ScoreRowSrc {
   int n;
   template <class F>
   __device__ void for_each(F f) const {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) f(make_key(s[i], static_cast<uint32_t>(i)));
+    // 8 independent loads in flight per thread (one load per iteration would be latency-bound)
+    const int stride = blockDim.x;
+    int i = threadIdx.x;
+    for (; i + 7 * stride < n; i += 8 * stride) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = s[i + j * stride];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f(make_key(v[j], static_cast<uint32_t>(i + j * stride)));
+    }
+    for (; i < n; i += stride) f(make_key(s[i], static_cast<uint32_t>(i)));
   }
 };
 __global__ void __launch_bounds__(256) tau_from_scores_kernel(const float* __restrict__ scores, int64_t ld, int n_valid,
@@ -228,10 +268,12 @@ __global__ void __launch_bounds__(128) canon_score_kernel(
     const uint32_t* __restrict__ n_cand, int keep, int64_t all_n, uint64_t* __restrict__ keys2,
     int64_t keys2_pitch, uint32_t* __restrict__ max_err_bits) {
   constexpr int kWarps = 4;
-  constexpr int kWordsPerRow = (sizeof(RowT) == 2) ? 32 : 64;  // 64 elements per chunk
-  constexpr int kPitch = kWordsPerRow + 1;
+  constexpr int kWords = 64;                                   // 32-bit words per row chunk (256 B)
+  constexpr int kElems = kWords * 4 / static_cast<int>(sizeof(RowT));  // 128 bf16 or 64 fp32 per chunk
+  constexpr int kPitch = kWords + 1;                           // conflict-free row walk
+  constexpr int kLoads = 16;                                   // warp loads per chunk (2 rows x 16 uint4 each)
   __shared__ uint32_t tile[kWarps][32 * kPitch];
-  __shared__ float qs[kWarps][64];
+  __shared__ double qs[kWarps][kElems];   // the query chunk, already widened to fp64
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qslot = blockIdx.y;                       // index into the selected-query list
   const int q = (qsel != nullptr) ? qsel[qslot] : qslot;
@@ -240,11 +282,10 @@ __global__ void __launch_bounds__(128) canon_score_kernel(
   const int64_t limit = (cand_keys != nullptr) ? static_cast<int64_t>(n_cand[q]) : all_n;
   const int64_t slots = (cand_keys != nullptr) ? keep : all_n;
   if (first >= slots) return;
-  // row id of this lane
   const int64_t slot = first + lane;
   uint32_t id = 0;
   float gemm_score = 0.f;
-  bool valid = slot < limit;
+  const bool valid = slot < limit;
   if (valid) {
     if (cand_keys != nullptr) {
       const uint64_t k = cand_keys[static_cast<int64_t>(q) * keep + slot];
@@ -254,44 +295,77 @@ __global__ void __launch_bounds__(128) canon_score_kernel(
       id = static_cast<uint32_t>(slot);
     }
   }
+  // this lane loads the 16-byte piece (lane & 15) of rows (lane >> 4) + 2*it, it = 0..15
+  const int v = lane & 15;
+  const uint8_t* src[kLoads];
+#pragma unroll
+  for (int it = 0; it < kLoads; ++it) {
+    const int r = it * 2 + (lane >> 4);
+    const uint32_t rid = __shfl_sync(0xFFFFFFFFu, id, r);
+    const bool rvalid = __shfl_sync(0xFFFFFFFFu, valid ? 1 : 0, r) != 0;
+    src[it] = rvalid ? reinterpret_cast<const uint8_t*>(rows + static_cast<int64_t>(rid) * row_pitch) + v * 16 : nullptr;
+  }
+  const int vec_elems = 16 / static_cast<int>(sizeof(RowT));
   const float* qv = qcanon + static_cast<int64_t>(q) * dp;
   double acc = 0.0;
   uint32_t* my_tile = tile[warp];
-  for (int c0 = 0; c0 < dp; c0 += 64) {
-    // stage: every 16-byte piece of the 32 row chunks, coalesced per row
-    constexpr int kVecPerRow = kWordsPerRow / 4;           // uint4 per row chunk (8 or 16)
-    constexpr int kRowsPerLoad = 32 / kVecPerRow;          // rows covered by one warp load (4 or 2)
+  uint4 pre[kLoads];
+  auto fetch = [&](int c0) {
 #pragma unroll
-    for (int it = 0; it < 32 / kRowsPerLoad; ++it) {
-      const int r = it * kRowsPerLoad + lane / kVecPerRow;
-      const int v = lane % kVecPerRow;
-      const uint32_t rid = __shfl_sync(0xFFFFFFFFu, id, r);
-      const bool rvalid = __shfl_sync(0xFFFFFFFFu, valid ? 1 : 0, r) != 0;
-      uint4 w = make_uint4(0, 0, 0, 0);
-      if (rvalid) {
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(rows + static_cast<int64_t>(rid) * row_pitch + c0);
-        w = ptx::ld_nc_u4(src + v * 16);
-      }
-      uint32_t* dst = my_tile + r * kPitch + v * 4;
-      dst[0] = w.x; dst[1] = w.y; dst[2] = w.z; dst[3] = w.w;
+    for (int it = 0; it < kLoads; ++it) {
+      pre[it] = make_uint4(0, 0, 0, 0);
+      if (src[it] != nullptr && c0 + v * vec_elems < dp)
+        pre[it] = ptx::ld_nc_u4(src[it] + static_cast<size_t>(c0) * sizeof(RowT));
     }
-    qs[warp][lane] = qv[c0 + lane];
-    qs[warp][lane + 32] = qv[c0 + lane + 32];
+  };
+  fetch(0);
+  for (int c0 = 0; c0 < dp; c0 += kElems) {
+#pragma unroll
+    for (int it = 0; it < kLoads; ++it) {
+      uint32_t* dst = my_tile + (it * 2 + (lane >> 4)) * kPitch + v * 4;
+      dst[0] = pre[it].x; dst[1] = pre[it].y; dst[2] = pre[it].z; dst[3] = pre[it].w;
+    }
+    for (int e = lane; e < kElems; e += 32) qs[warp][e] = (c0 + e < dp) ? static_cast<double>(qv[c0 + e]) : 0.0;
     __syncwarp();
+    if (c0 + kElems < dp) fetch(c0 + kElems);          // next chunk in flight while this one is summed
     const uint32_t* mine = my_tile + lane * kPitch;
-    if (sizeof(RowT) == 2) {
-#pragma unroll 8
-      for (int w = 0; w < 32; ++w) {
-        const uint32_t u = mine[w];
-        const float x0 = __uint_as_float(u << 16);
-        const float x1 = __uint_as_float(u & 0xFFFF0000u);
-        acc = fma(static_cast<double>(qs[warp][2 * w]), static_cast<double>(x0), acc);
-        acc = fma(static_cast<double>(qs[warp][2 * w + 1]), static_cast<double>(x1), acc);
-      }
-    } else {
-#pragma unroll 8
-      for (int w = 0; w < 64; ++w) {
-        acc = fma(static_cast<double>(qs[warp][w]), static_cast<double>(__uint_as_float(mine[w])), acc);
+    // batches of 8 words: all shared loads and widenings first, then the dependent fp64 chain
+#pragma unroll 1
+    for (int w0 = 0; w0 < kWords; w0 += 8) {
+      uint32_t u[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] = mine[w0 + i];
+      uint32_t odd = 0;
+      if (sizeof(RowT) == 2) {
+        double xd[16], qd[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) qd[i] = qs[warp][2 * w0 + i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xd[2 * i] = widen_f32_bits(u[i] << 16, odd);
+          xd[2 * i + 1] = widen_f32_bits(u[i] & 0xFFFF0000u, odd);
+        }
+        if (odd) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            xd[2 * i] = static_cast<double>(__uint_as_float(u[i] << 16));
+            xd[2 * i + 1] = static_cast<double>(__uint_as_float(u[i] & 0xFFFF0000u));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc = fma(qd[i], xd[i], acc);
+      } else {
+        double xd[8], qd[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qd[i] = qs[warp][w0 + i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xd[i] = widen_f32_bits(u[i], odd);
+        if (odd) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xd[i] = static_cast<double>(__uint_as_float(u[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fma(qd[i], xd[i], acc);
       }
     }
     __syncwarp();

@@ -12,7 +12,7 @@ struct SelectSmem {
   uint64_t keys[kSortCap];
   uint32_t hist[256];
   uint32_t ctr;
-  uint32_t digit, before, cnt;
+  uint32_t digit, before, cnt, seen;
 };
 
 __device__ __forceinline__ uint32_t next_pow2(uint32_t x) {
@@ -24,7 +24,7 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t x) {
 // warp 0: find the bin holding the `remaining`-th largest key given the 256-bin histogram
 __device__ __forceinline__ void hist_find_bin(const uint32_t* hist, uint32_t remaining,
                                               uint32_t lane, uint32_t* o_digit,
-                                              uint32_t* o_before, uint32_t* o_cnt) {
+                                              uint32_t* o_before, uint32_t* o_cnt, uint32_t* o_seen) {
   uint32_t c[8];
   uint32_t mine = 0;
 #pragma unroll
@@ -36,6 +36,7 @@ __device__ __forceinline__ void hist_find_bin(const uint32_t* hist, uint32_t rem
     if (lane + o < 32) incl += t;
   }
   const uint32_t above = incl - mine;
+  if (lane == 0) *o_seen = incl;   // keys counted in this pass
   if (above < remaining && remaining <= above + mine) {
     uint32_t run = above;
 #pragma unroll
@@ -50,17 +51,84 @@ __device__ __forceinline__ void hist_find_bin(const uint32_t* hist, uint32_t rem
   }
 }
 
+// Selection among the n keys already staged in sm->keys[0..n): leaves the min(n,k) best sorted
+// descending at the front and returns that count.  blockDim.x must be 256, n <= kSortCap.
+// Above 1024 keys a full sort is wasteful: the k-th largest of the 256 per-thread maxima is a lower
+// bound of the k-th largest key, so only keys at or above it (about k of them) need sorting.
+__device__ __forceinline__ uint32_t block_topk_smem(SelectSmem* sm, uint32_t n, uint32_t k) {
+  const uint32_t tid = threadIdx.x;
+  constexpr uint32_t kPer = kSortCap / 256;
+  if (n > 1024 && k < n && k <= 256) {
+    uint64_t mine[kPer];
+    uint64_t mx = 0ull;
+#pragma unroll
+    for (uint32_t j = 0; j < kPer; ++j) {
+      const uint32_t i = tid + j * 256;
+      mine[j] = (i < n) ? sm->keys[i] : 0ull;
+      mx = mine[j] > mx ? mine[j] : mx;
+    }
+    __syncthreads();
+    sm->keys[tid] = mx;
+    block_bitonic_desc(sm->keys, 256);
+    const uint64_t t0 = sm->keys[k - 1];
+    if (tid == 0) sm->ctr = 0;
+    __syncthreads();
+#pragma unroll
+    for (uint32_t j = 0; j < kPer; ++j) {
+      if (mine[j] >= t0 && mine[j] != 0ull) sm->keys[atomicAdd(&sm->ctr, 1u)] = mine[j];
+    }
+    __syncthreads();
+    n = sm->ctr;
+  }
+  const uint32_t np = max(next_pow2(n), 2u);
+  for (uint32_t i = n + tid; i < np; i += blockDim.x) sm->keys[i] = 0ull;
+  block_bitonic_desc(sm->keys, np);
+  return min(n, k);
+}
+
 // Src: struct with   template<class F> __device__ void for_each(F f) const
 // calling f(key) for the keys assigned to this thread (each key visited by exactly one thread).
 // Leaves the min(total,k) best keys sorted descending in sm->keys[0..); returns that count.
-// Keys must be distinct and != 0.  k <= kSortCap.  All threads of the block must call.
+// Keys must be distinct and != 0.  k <= kSortCap.  All 256 threads of the block must call.
 template <class Src>
 __device__ uint32_t block_topk(const Src& src, uint32_t total, uint32_t k, SelectSmem* sm) {
   const uint32_t tid = threadIdx.x;
+  if (total <= kSortCap) {
+    // stage once, select in shared memory
+    if (tid == 0) sm->ctr = 0;
+    __syncthreads();
+    src.for_each([&](uint64_t key) {
+      if (key != 0ull) {
+        const uint32_t pos = atomicAdd(&sm->ctr, 1u);
+        if (pos < kSortCap) sm->keys[pos] = key;
+      }
+    });
+    __syncthreads();
+    return block_topk_smem(sm, min(sm->ctr, kSortCap), k);
+  }
   uint64_t thresh = 0;  // keep keys >= thresh
-  uint32_t n_keep = total;
-  if (total > kSortCap) {
-    // MSD radix walk for the exact k-th largest key
+  bool have_thresh = false;
+  if (k <= 256) {
+    // streaming variant of the per-thread-maximum bound: two passes over the source
+    uint64_t mx = 0ull;
+    src.for_each([&](uint64_t key) { mx = key > mx ? key : mx; });
+    sm->keys[tid] = mx;
+    block_bitonic_desc(sm->keys, 256);
+    const uint64_t t0 = sm->keys[k - 1];
+    if (tid == 0) sm->ctr = 0;
+    __syncthreads();
+    src.for_each([&](uint64_t key) {
+      if (key >= t0 && key != 0ull) {
+        const uint32_t pos = atomicAdd(&sm->ctr, 1u);
+        if (pos < kSortCap) sm->keys[pos] = key;
+      }
+    });
+    __syncthreads();
+    if (sm->ctr <= kSortCap) return block_topk_smem(sm, sm->ctr, k);
+    __syncthreads();   // masses of ties above the bound: fall through to the exact radix walk
+  }
+  {
+    // MSD radix walk over the 64-bit keys for the exact k-th largest key (<= 8 passes)
     uint64_t prefix = 0;
     uint32_t remaining = k;
     for (int shift = 56; shift >= 0; shift -= 8) {
@@ -68,11 +136,16 @@ __device__ uint32_t block_topk(const Src& src, uint32_t total, uint32_t k, Selec
       __syncthreads();
       const uint64_t himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
       src.for_each([&](uint64_t key) {
-        if ((key & himask) == prefix) atomicAdd(&sm->hist[(key >> shift) & 0xFF], 1u);
+        if ((key & himask) == prefix && key != 0ull) atomicAdd(&sm->hist[(key >> shift) & 0xFF], 1u);
       });
       __syncthreads();
-      if (tid < 32) hist_find_bin(sm->hist, remaining, tid, &sm->digit, &sm->before, &sm->cnt);
+      if (tid < 32) hist_find_bin(sm->hist, remaining, tid, &sm->digit, &sm->before, &sm->cnt, &sm->seen);
       __syncthreads();
+      if (sm->seen <= remaining) {   // fewer real keys than asked for (padding in the source): keep them all
+        __syncthreads();
+        prefix = 0;
+        break;
+      }
       prefix |= static_cast<uint64_t>(sm->digit) << shift;
       remaining -= sm->before;
       const bool stop = (sm->cnt == remaining) || shift == 0;
@@ -80,23 +153,19 @@ __device__ uint32_t block_topk(const Src& src, uint32_t total, uint32_t k, Selec
       if (stop) break;
     }
     thresh = prefix;
-    n_keep = k;
+    have_thresh = true;
   }
+  (void)have_thresh;
   if (tid == 0) sm->ctr = 0;
   __syncthreads();
   src.for_each([&](uint64_t key) {
     if (key >= thresh && key != 0ull) {
-      uint32_t pos = atomicAdd(&sm->ctr, 1u);
+      const uint32_t pos = atomicAdd(&sm->ctr, 1u);
       if (pos < kSortCap) sm->keys[pos] = key;
     }
   });
   __syncthreads();
-  uint32_t n = min(sm->ctr, kSortCap);
-  (void)n_keep;
-  const uint32_t np = max(next_pow2(n), 2u);
-  for (uint32_t i = n + tid; i < np; i += blockDim.x) sm->keys[i] = 0ull;
-  block_bitonic_desc(sm->keys, np);
-  return min(n, k);
+  return block_topk_smem(sm, min(sm->ctr, kSortCap), k);
 }
 
 }  // namespace vfi

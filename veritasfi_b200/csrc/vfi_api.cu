@@ -121,14 +121,29 @@ int make_tmap(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, in
   return VFI_OK;
 }
 
+// cudaGetDeviceProperties costs milliseconds: query each device once
 int device_props(int device, cudaDeviceProp* prop) {
-  int n = 0;
-  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
-    cudaGetLastError();
-    return fail(VFI_ERR_NO_DEVICE, "no CUDA device: this library has no CPU implementation");
+  static std::mutex mu;
+  static std::vector<cudaDeviceProp> cache;
+  static std::vector<char> have;
+  static int n_dev = -1;
+  std::lock_guard<std::mutex> lock(mu);
+  if (n_dev < 0) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      return fail(VFI_ERR_NO_DEVICE, "no CUDA device: this library has no CPU implementation");
+    }
+    n_dev = n;
+    cache.resize(n);
+    have.assign(n, 0);
   }
-  if (device < 0 || device >= n) return fail(VFI_ERR_INVALID, "device index out of range");
-  VFI_CUDA(cudaGetDeviceProperties(prop, device));
+  if (device < 0 || device >= n_dev) return fail(VFI_ERR_INVALID, "device index out of range");
+  if (!have[device]) {
+    VFI_CUDA(cudaGetDeviceProperties(&cache[device], device));
+    have[device] = 1;
+  }
+  *prop = cache[device];
   if (prop->major != 10)
     return fail(VFI_ERR_NO_DEVICE, std::string("device '") + prop->name + "' is not sm_100 (kernels are built for sm_100a only)");
   return VFI_OK;
@@ -473,8 +488,8 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
   p.scores_out = scores_out;
   p.ld_scores = ld_scores;
   if (mode == vfi::MODE_TOPK) {
-    VFI_TRY(idx->w_cand.ensure(static_cast<size_t>(n_groups) * nq_pad * cap * 8));
-    VFI_TRY(idx->w_cand_count.ensure(static_cast<size_t>(n_groups) * nq_pad * 4));
+    VFI_TRY(idx->w_cand.ensure(static_cast<size_t>(2 * n_groups) * nq_pad * cap * 8));
+    VFI_TRY(idx->w_cand_count.ensure(static_cast<size_t>(2 * n_groups) * nq_pad * 4));
     p.cand = idx->w_cand.as<uint64_t>();
     p.cand_count = idx->w_cand_count.as<uint32_t>();
   }
@@ -489,7 +504,7 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
   if (prof) cudaEventRecord(idx->ev1, st);
   VFI_CUDA(cudaGetLastError());
   if (profile) idx->stats.fused_launches++;
-  if (o_groups) *o_groups = n_groups;
+  if (o_groups) *o_groups = 2 * n_groups;   // one key buffer per (group, epilogue set)
   if (o_nq_pad) *o_nq_pad = nq_pad;
   if (o_cap) *o_cap = cap;
   return VFI_OK;
@@ -1019,7 +1034,7 @@ int vfi_bm25_search(vfi_bm25_t* b, const int32_t* q_tokens, const int64_t* q_ind
   const size_t smem = ((sizeof(vfi::Bm25Smem) + 15) & ~size_t(15)) + static_cast<size_t>(cap) * 8;
   const int n_ctas = b->num_sms * 2;
   const int64_t n_tiles = std::max<int64_t>(1, ceil_div(b->n_docs, vfi::kBmTile));
-  int64_t n_seg = std::min<int64_t>(n_tiles, std::max<int64_t>(1, ceil_div(static_cast<int64_t>(8) * n_ctas, nq)));
+  int64_t n_seg = std::min<int64_t>(std::min<int64_t>(n_tiles, 1024), std::max<int64_t>(1, ceil_div(static_cast<int64_t>(8) * n_ctas, nq)));
   const int64_t seg_docs = ceil_div(n_tiles, n_seg) * vfi::kBmTile;
   n_seg = std::max<int64_t>(1, ceil_div(b->n_docs, seg_docs));
   VFI_TRY(b->w_tok.ensure(std::max<size_t>(16, static_cast<size_t>(n_tok) * 4)));
