@@ -438,67 +438,104 @@ __global__ void __launch_bounds__(256) finalize_kernel(
 // k' keys per (CTA, query) in the same layout the fused kernel uses, so K1c/K2 are shared.
 // ------------------------------------------------------------------------------------------
 constexpr int kGemvThreads = 512;               // 16 warps
-constexpr int kGemvRowsPerRound = 16 * 8;       // each warp scores 8 rows per round
+constexpr int kGemvRowsPerWarp = 16;            // rows a warp scores per round
+constexpr int kGemvRowsPerRound = 16 * kGemvRowsPerWarp;
 constexpr int kGemvMaxQ = 8;
+constexpr int kGemvIlp = 4;                     // rows whose loads are in flight together per warp
+constexpr int kGemvMaxVec = 4;                  // 16-byte pieces per lane per row handled in registers (d <= 1024 bf16 / 512 fp32)
 
-template <typename RowT>
+template <typename RowT, int NQ>
+__device__ __forceinline__ void gemv_rows(const RowT* __restrict__ rows, int64_t row_pitch, int vecs, int64_t row0,
+                                          int n_valid, const float* __restrict__ sq, int dp, uint32_t lane,
+                                          float (&out)[kGemvIlp][NQ]) {
+  constexpr int kE = 16 / sizeof(RowT);
+  uint4 w[kGemvIlp][kGemvMaxVec];
+  // all loads of the row group first
+#pragma unroll
+  for (int r = 0; r < kGemvIlp; ++r) {
+    const uint8_t* rp = reinterpret_cast<const uint8_t*>(rows + (row0 + r) * row_pitch);
+#pragma unroll
+    for (int i = 0; i < kGemvMaxVec; ++i) {
+      const int v = lane + 32 * i;
+      w[r][i] = (r < n_valid && v < vecs) ? ptx::ld_nc_u4(rp + static_cast<size_t>(v) * 16) : make_uint4(0, 0, 0, 0);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kGemvIlp; ++r)
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) out[r][j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < kGemvMaxVec; ++i) {
+    const int v = lane + 32 * i;
+    if (v < vecs) {
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) {
+        float qv[kE];
+        const float4* q4 = reinterpret_cast<const float4*>(sq + j * dp + v * kE);
+        const float4 a = q4[0];
+        qv[0] = a.x; qv[1] = a.y; qv[2] = a.z; qv[3] = a.w;
+        if (kE == 8) {
+          const float4 b = q4[1];
+          qv[4] = b.x; qv[5] = b.y; qv[6] = b.z; qv[7] = b.w;
+        }
+#pragma unroll
+        for (int r = 0; r < kGemvIlp; ++r) {
+          float x[8];
+          const uint4 u = w[r][i];
+          if (sizeof(RowT) == 2) {
+            x[0] = __uint_as_float(u.x << 16); x[1] = __uint_as_float(u.x & 0xFFFF0000u);
+            x[2] = __uint_as_float(u.y << 16); x[3] = __uint_as_float(u.y & 0xFFFF0000u);
+            x[4] = __uint_as_float(u.z << 16); x[5] = __uint_as_float(u.z & 0xFFFF0000u);
+            x[6] = __uint_as_float(u.w << 16); x[7] = __uint_as_float(u.w & 0xFFFF0000u);
+          } else {
+            x[0] = __uint_as_float(u.x); x[1] = __uint_as_float(u.y);
+            x[2] = __uint_as_float(u.z); x[3] = __uint_as_float(u.w);
+          }
+#pragma unroll
+          for (int e = 0; e < kE; ++e) out[r][j] = fmaf(qv[e], x[e], out[r][j]);
+        }
+      }
+    }
+  }
+}
+
+template <typename RowT, int NQ>
 __global__ void __launch_bounds__(kGemvThreads) gemv_topk_kernel(
     const RowT* __restrict__ rows, int64_t row_pitch, int dp, int64_t n_rows,
-    const float* __restrict__ qcanon, int nq, int keep, int cap /*pow2 >= keep + rows/round*/,
+    const float* __restrict__ qcanon, int keep, int cap /*pow2 >= keep + rows/round*/,
     uint64_t* __restrict__ cand, uint32_t* __restrict__ cand_count, int nq_pad, int cand_cap) {
   extern __shared__ uint8_t smem_raw[];
-  // layout: q fp32 [nq][dp] | keys [nq][cap] | counts [nq] | tau [nq]
+  // layout: q fp32 [NQ][dp] | keys [NQ][cap] | counts | tau
   float* sq = reinterpret_cast<float*>(smem_raw);
-  uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw + ((static_cast<size_t>(nq) * dp * 4 + 15) & ~size_t(15)));
-  uint32_t* scount = reinterpret_cast<uint32_t*>(skeys + static_cast<size_t>(nq) * cap);
+  uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw + ((static_cast<size_t>(NQ) * dp * 4 + 15) & ~size_t(15)));
+  uint32_t* scount = reinterpret_cast<uint32_t*>(skeys + static_cast<size_t>(NQ) * cap);
   uint64_t* stau = reinterpret_cast<uint64_t*>(scount + 2 * kGemvMaxQ);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < nq * dp; i += blockDim.x) sq[i] = qcanon[i];
+  for (int i = threadIdx.x; i < NQ * dp; i += blockDim.x) sq[i] = qcanon[i];
   if (threadIdx.x < kGemvMaxQ) { scount[threadIdx.x] = 0; stau[threadIdx.x] = kKeyNone; }
   __syncthreads();
 
-  constexpr int kElemsPerVec = 16 / sizeof(RowT);  // 8 bf16 or 4 fp32 per 16-byte load
-  const int vecs = dp / kElemsPerVec;               // dp is a multiple of 64
+  constexpr int kE = 16 / sizeof(RowT);
+  const int vecs = dp / kE;               // dp is a multiple of 64
   const int64_t n_rounds = (n_rows + kGemvRowsPerRound - 1) / kGemvRowsPerRound;
   for (int64_t round = blockIdx.x; round < n_rounds; round += gridDim.x) {
-    const int64_t base = round * kGemvRowsPerRound + warp * 8;
+    const int64_t base = round * kGemvRowsPerRound + warp * kGemvRowsPerWarp;
 #pragma unroll 1
-    for (int r = 0; r < 8; ++r) {
-      const int64_t row = base + r;
-      if (row >= n_rows) break;
-      float acc[kGemvMaxQ];
+    for (int r0 = 0; r0 < kGemvRowsPerWarp; r0 += kGemvIlp) {
+      const int64_t row0 = base + r0;
+      if (row0 >= n_rows) break;
+      const int n_valid = static_cast<int>(min(static_cast<int64_t>(kGemvIlp), n_rows - row0));
+      float acc[kGemvIlp][NQ];
+      gemv_rows<RowT, NQ>(rows, row_pitch, vecs, row0, n_valid, sq, dp, lane, acc);
 #pragma unroll
-      for (int j = 0; j < kGemvMaxQ; ++j) acc[j] = 0.f;
-      const uint8_t* rp = reinterpret_cast<const uint8_t*>(rows + row * row_pitch);
-      for (int v = lane; v < vecs; v += 32) {
-        const uint4 w = ptx::ld_nc_u4(rp + static_cast<size_t>(v) * 16);
-        float x[8];
-        if (sizeof(RowT) == 2) {
-          x[0] = __uint_as_float(w.x << 16); x[1] = __uint_as_float(w.x & 0xFFFF0000u);
-          x[2] = __uint_as_float(w.y << 16); x[3] = __uint_as_float(w.y & 0xFFFF0000u);
-          x[4] = __uint_as_float(w.z << 16); x[5] = __uint_as_float(w.z & 0xFFFF0000u);
-          x[6] = __uint_as_float(w.w << 16); x[7] = __uint_as_float(w.w & 0xFFFF0000u);
-        } else {
-          x[0] = __uint_as_float(w.x); x[1] = __uint_as_float(w.y);
-          x[2] = __uint_as_float(w.z); x[3] = __uint_as_float(w.w);
-        }
+      for (int r = 0; r < kGemvIlp; ++r) {
 #pragma unroll
-        for (int j = 0; j < kGemvMaxQ; ++j) {
-          if (j < nq) {
-            const float* qj = sq + j * dp + v * kElemsPerVec;
+        for (int j = 0; j < NQ; ++j) {
+          float sres = acc[r][j];
 #pragma unroll
-            for (int e = 0; e < kElemsPerVec; ++e) acc[j] = fmaf(qj[e], x[e], acc[j]);
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < kGemvMaxQ; ++j) {
-        if (j < nq) {
-          float s = acc[j];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-          if (lane == 0) {
-            const uint64_t key = make_key(s, static_cast<uint32_t>(row));
+          for (int o = 16; o > 0; o >>= 1) sres += __shfl_xor_sync(0xFFFFFFFFu, sres, o);
+          if (lane == 0 && r < n_valid) {
+            const uint64_t key = make_key(sres, static_cast<uint32_t>(row0 + r));
             if (key > stau[j]) {
               const uint32_t pos = atomicAdd(&scount[j], 1u);
               skeys[static_cast<size_t>(j) * cap + pos] = key;   // pos < cap by construction
@@ -509,7 +546,7 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_topk_kernel(
     }
     __syncthreads();
     // compact any buffer that could overflow in the next round
-    for (int j = 0; j < nq; ++j) {
+    for (int j = 0; j < NQ; ++j) {
       const uint32_t c = scount[j];
       if (c + kGemvRowsPerRound > static_cast<uint32_t>(cap)) {
         uint64_t* kj = skeys + static_cast<size_t>(j) * cap;
@@ -522,7 +559,7 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_topk_kernel(
   }
   // emit: sort what is left and write the best k' of each query
   __syncthreads();
-  for (int j = 0; j < nq; ++j) {
+  for (int j = 0; j < NQ; ++j) {
     const uint32_t c = scount[j];
     uint64_t* kj = skeys + static_cast<size_t>(j) * cap;
     for (uint32_t i = c + threadIdx.x; i < static_cast<uint32_t>(cap); i += blockDim.x) kj[i] = 0ull;

@@ -5,11 +5,7 @@
 //
 // K4 restates bm25s.BM25.retrieve called at /root/reference/src/utils/bm25Retriever.py:75-79:
 // scores[doc] starts at +0 and receives the precomputed impact of every query token, in query
-// token order, in fp32 (np.add.at order).  To reproduce that order without atomics each CTA
-// sweeps a doc range tile by tile; inside a tile every active token scatters its impacts into
-// its own shared-memory plane (a doc occurs at most once per posting list => one writer per
-// cell), and the planes are then summed per doc in token order.  x + 0.0f == x, so tokens that
-// do not touch a doc can be skipped without changing a bit.
+// token order, in fp32 (np.add.at order).
 #pragma once
 #include <limits.h>
 
@@ -19,12 +15,22 @@
 
 namespace vfi {
 
-constexpr int kBmTile = 2048;     // docs per tile
-constexpr int kBmPlanes = 8;      // token planes resident per pass
-constexpr int kBmThreads = 512;
+// ---- K4: BM25 over doc ranges ------------------------------------------------------------
+// Work item = (query, doc segment); a CTA sweeps the segment in ranges of 8192 docs whose fp32
+// accumulator lives in shared memory.  Inside a range the query's tokens are applied ONE AFTER THE
+// OTHER (a block barrier between tokens), each token's postings streamed by all threads with
+// several loads in flight per thread: a doc occurs once per posting list, so the adds of one token
+// never collide, and the barrier fixes the per-doc order to query-token order — np.add.at's fp32
+// result bit for bit, without atomics.  All posting offsets of the segment (token x range boundary)
+// are found by parallel binary searches once per work item, so the sweep itself has no searches,
+// no speculation and no per-tile bookkeeping.
+constexpr int kBmRange = 8192;    // docs per range (32 KB accumulator)
+constexpr int kBmThreads = 256;
 constexpr int kBmMaxTok = 64;     // tokens per query handled by the kernel
-constexpr int kBmPiece = 256;     // postings per warp work piece
+constexpr int kBmMaxRanges = 8;   // ranges per segment
 constexpr int kBmScan = 1024;     // docs scanned between buffer-compaction checks
+constexpr int kBmUnroll = 16;     // postings per thread in flight while a heavy token streams
+constexpr int kBmLight = 8;       // light postings per thread prefetched per range (all light tokens at once)
 
 struct Bm25Params {
   const int64_t* indptr;
@@ -32,7 +38,7 @@ struct Bm25Params {
   const float* data;
   int64_t n_docs;
   int n_seg;              // doc segments per query (work item = query x segment)
-  int64_t seg_docs;       // docs per segment (multiple of kBmTile)
+  int64_t seg_docs;       // docs per segment (multiple of kBmRange, at most kBmMaxRanges ranges)
   const int32_t* q_tokens;
   const int64_t* q_indptr;
   int nq, nq_pad;
@@ -42,23 +48,19 @@ struct Bm25Params {
   uint64_t* cand;         // [n_seg][nq_pad][keep]
   uint32_t* cand_count;   // [n_seg][nq_pad]
   uint32_t* work_counter;
+  unsigned long long* qtau;  // [nq] best published threshold key per query, shared by its work items (zeroed per search)
   float* dump;            // != nullptr: write all scores of query 0 here instead of selecting
 };
 
 struct Bm25Smem {
-  float planes[kBmPlanes][kBmTile];
-  float acc[kBmTile];
-  int64_t cur[kBmMaxTok];
-  int64_t end[kBmMaxTok];
-  float dens[kBmMaxTok];
-  int next_doc[kBmMaxTok];
-  int act[kBmMaxTok];
-  int64_t win[kBmPlanes];        // window length per plane token this round
-  int piece_start[kBmPlanes + 1];
-  uint32_t adv[kBmPlanes];
-  int n_act;
-  int min_next;
-  int more;
+  float acc[kBmRange];
+  int64_t offs[kBmMaxTok][kBmMaxRanges + 1];   // posting offset of token t at range boundary r
+  uint32_t pref[kBmMaxTok + 1];                // exclusive prefix of the per-token posting counts of the current range
+  uint32_t lstart[kBmMaxTok];                  // flat start of token t among the prefetched light tokens, or ~0
+  uint32_t lpre[kBmMaxTok + 1];                // the same starts, compacted over the light tokens only
+  uint8_t ltok[kBmMaxTok];                     // token index of the i-th light token
+  int n_light;
+  uint32_t overflow;
   uint32_t count;
   uint64_t tau;
   uint32_t work;
@@ -72,12 +74,11 @@ __device__ __forceinline__ int64_t lower_bound_i32(const int32_t* a, int64_t lo,
   return lo;
 }
 
-__global__ void __launch_bounds__(kBmThreads, 2) bm25_kernel(const Bm25Params p) {
+__global__ void __launch_bounds__(kBmThreads, 4) bm25_kernel(const Bm25Params p) {
   extern __shared__ uint8_t smem_raw[];
   Bm25Smem* sm = reinterpret_cast<Bm25Smem*>(smem_raw);
   uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(Bm25Smem) + 15) & ~size_t(15)));
-  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr uint32_t kWarps = kBmThreads / 32;
+  const uint32_t tid = threadIdx.x;
   const uint32_t n_work = static_cast<uint32_t>(p.nq) * p.n_seg;
 
   for (;;) {
@@ -86,159 +87,235 @@ __global__ void __launch_bounds__(kBmThreads, 2) bm25_kernel(const Bm25Params p)
     __syncthreads();
     const uint32_t w = sm->work;
     if (w >= n_work) break;
-    const int q = w / p.n_seg;
-    const int seg = w % p.n_seg;
+    // segment-major order: by the time a query's next segment starts, an earlier one has usually
+    // published a threshold, so the warm-up (everything admitted, repeated compactions) is paid once
+    const int seg = w / p.nq;
+    const int q = w % p.nq;
     const int64_t d0 = static_cast<int64_t>(seg) * p.seg_docs;
     const int64_t d1 = min(d0 + p.seg_docs, p.n_docs);
+    const int R = static_cast<int>((d1 - d0 + kBmRange - 1) / kBmRange);
     const int64_t tq0 = p.q_indptr[q];
     const int T = static_cast<int>(p.q_indptr[q + 1] - tq0);
-    // posting range of every token inside this doc segment
-    if (tid < T) {
-      const int32_t tok = p.q_tokens[tq0 + tid];
-      const int64_t lo = p.indptr[tok], hi = p.indptr[tok + 1];
-      const int64_t s = lower_bound_i32(p.indices, lo, hi, d0);
-      const int64_t e = lower_bound_i32(p.indices, s, hi, d1);
-      sm->cur[tid] = s;
-      sm->end[tid] = e;
-      sm->dens[tid] = static_cast<float>(e - s) / static_cast<float>((d1 - d0) > 0 ? (d1 - d0) : 1);
+    // every (token, range boundary) offset by an independent binary search
+    for (int i = tid; i < T * (R + 1); i += kBmThreads) {
+      const int t = i / (R + 1), r = i % (R + 1);
+      const int32_t tok = p.q_tokens[tq0 + t];
+      const int64_t bound = min(d0 + static_cast<int64_t>(r) * kBmRange, d1);
+      sm->offs[t][r] = lower_bound_i32(p.indices, p.indptr[tok], p.indptr[tok + 1], bound);
     }
-    if (tid == 0) { sm->count = 0; sm->tau = kKeyNone; }
+    if (tid == 0) { sm->count = 0; sm->tau = (p.qtau != nullptr) ? p.qtau[q] : kKeyNone; }
+    for (int i = tid; i < kBmRange; i += kBmThreads) sm->acc[i] = 0.f;
     __syncthreads();
 
-    int64_t tile_start = d0;
-    while (tile_start < d1) {
-      // next doc of every token; jump over tiles no token touches
-      if (tid == 0) sm->min_next = INT_MAX;
-      __syncthreads();
-      if (tid < T) {
-        const int nd = (sm->cur[tid] < sm->end[tid]) ? p.indices[sm->cur[tid]] : INT_MAX;
-        sm->next_doc[tid] = nd;
-        if (nd != INT_MAX) atomicMin(&sm->min_next, nd);
-      }
-      __syncthreads();
-      if (p.all_positive && p.dump == nullptr) {
-        if (sm->min_next == INT_MAX) break;
-        const int64_t jump = (static_cast<int64_t>(sm->min_next) / kBmTile) * kBmTile;
-        tile_start = max(tile_start, jump);
-      }
-      const int64_t tile_end = min(tile_start + kBmTile, d1);
+    for (int r = 0; r < R; ++r) {
+      const int64_t rs = d0 + static_cast<int64_t>(r) * kBmRange;
+      const int64_t re = min(rs + kBmRange, d1);
+      const int range_docs = static_cast<int>(re - rs);
       if (tid == 0) {
-        int n = 0;
-        for (int t = 0; t < T; ++t)
-          if (static_cast<int64_t>(sm->next_doc[t]) < tile_end) sm->act[n++] = t;
-        sm->n_act = n;
+        uint32_t run = 0;
+        for (int t = 0; t < T; ++t) {
+          sm->pref[t] = run;
+          run += static_cast<uint32_t>(sm->offs[t][r + 1] - sm->offs[t][r]);
+        }
+        sm->pref[T] = run;
+        if (p.qtau != nullptr) {     // adopt a better threshold published by another segment of this query
+          const uint64_t g = *reinterpret_cast<volatile unsigned long long*>(p.qtau + q);
+          if (g > sm->tau) sm->tau = g;
+        }
       }
-      for (int i = tid; i < kBmTile; i += kBmThreads) sm->acc[i] = 0.f;
       __syncthreads();
-      const int n_act = sm->n_act;
-
-      for (int pass0 = 0; pass0 < n_act; pass0 += kBmPlanes) {
-        const int np = min(kBmPlanes, n_act - pass0);
-        for (int i = tid; i < np * kBmTile; i += kBmThreads) (&sm->planes[0][0])[i] = 0.f;
-        if (tid == 0) sm->more = 1;
-        __syncthreads();
-        while (sm->more) {
-          // size one speculative window per plane token and cut the windows into warp pieces
-          if (tid == 0) {
-            int ps = 0;
-            for (int j = 0; j < np; ++j) {
-              const int t = sm->act[pass0 + j];
-              const int64_t left = sm->end[t] - sm->cur[t];
-              int64_t wlen = 0;
-              if (left > 0 && static_cast<int64_t>(p.indices[sm->cur[t]]) < tile_end) {
-                const int64_t est = static_cast<int64_t>(sm->dens[t] * static_cast<float>(tile_end - tile_start) * 1.25f) + 64;
-                wlen = min(left, est);
-              }
-              sm->win[j] = wlen;
-              sm->piece_start[j] = ps;
-              ps += static_cast<int>((wlen + kBmPiece - 1) / kBmPiece);
-              sm->adv[j] = 0;
-            }
-            sm->piece_start[np] = ps;
-          }
-          __syncthreads();
-          const int n_pieces = sm->piece_start[np];
-          for (int piece = warp; piece < n_pieces; piece += kWarps) {
-            int j = 0;
-            while (piece >= sm->piece_start[j + 1]) ++j;
-            const int t = sm->act[pass0 + j];
-            const int64_t off = static_cast<int64_t>(piece - sm->piece_start[j]) * kBmPiece;
-            const int64_t base = sm->cur[t] + off;
-            const int n = static_cast<int>(min(static_cast<int64_t>(kBmPiece), sm->win[j] - off));
-            int32_t doc[kBmPiece / 32];
-            float val[kBmPiece / 32];
-#pragma unroll
-            for (int i = 0; i < kBmPiece / 32; ++i) {
-              const int o = i * 32 + lane;
-              doc[i] = (o < n) ? __ldg(p.indices + base + o) : INT_MAX;
-              val[i] = (o < n) ? __ldg(p.data + base + o) : 0.f;
-            }
-            uint32_t cnt = 0;
-            float* plane = sm->planes[j];
-#pragma unroll
-            for (int i = 0; i < kBmPiece / 32; ++i) {
-              if (static_cast<int64_t>(doc[i]) < tile_end) {
-                plane[doc[i] - tile_start] = val[i];
-                ++cnt;
-              }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
-            if (lane == 0 && cnt) atomicAdd(&sm->adv[j], cnt);
-          }
-          __syncthreads();
-          if (tid == 0) {
-            int more = 0;
-            for (int j = 0; j < np; ++j) {
-              const int t = sm->act[pass0 + j];
-              const bool exhausted_window = (sm->adv[j] == static_cast<uint32_t>(sm->win[j])) && sm->win[j] > 0;
-              sm->cur[t] += sm->adv[j];
-              if (exhausted_window && sm->cur[t] < sm->end[t]) more = 1;  // may continue in this tile
-            }
-            sm->more = more;
-          }
-          __syncthreads();
-        }
-        // fold the planes into the accumulator in token order
-        for (int i = tid; i < kBmTile; i += kBmThreads) {
-          float s = sm->acc[i];
-          for (int j = 0; j < np; ++j) s += sm->planes[j][i];
-          sm->acc[i] = s;
-        }
-        __syncthreads();
+      const uint32_t total = sm->pref[T];
+      if (total == 0 && p.all_positive && p.dump == nullptr) {   // no token touches this range
+        __syncthreads();                                           // (everyone has read pref before it is rewritten)
+        continue;
       }
 
-      const int tile_docs = static_cast<int>(tile_end - tile_start);
+      // Light tokens (<= 256 postings here) would each expose a full memory latency for a handful of
+      // postings: the light tokens' postings form one flat token-major sequence of at most
+      // 256 x kBmLight entries that is loaded up front with every load in flight.  Heavier tokens
+      // (and light ones beyond that capacity) are streamed when their turn comes.
+      constexpr uint32_t kLightCap = kBmThreads * kBmLight;
+      auto cnt_of = [&](int t) -> uint32_t { return sm->pref[t + 1] - sm->pref[t]; };
+      if (tid == 0) {
+        uint32_t run = 0;
+        int nl = 0;
+        for (int t = 0; t < T; ++t) {
+          const uint32_t c = cnt_of(t);
+          if (c > 0 && c <= 256u && run + c <= kLightCap) {
+            sm->lstart[t] = run;
+            sm->ltok[nl] = static_cast<uint8_t>(t);
+            sm->lpre[nl] = run;
+            ++nl;
+            run += c;
+          } else {
+            sm->lstart[t] = 0xFFFFFFFFu;
+          }
+        }
+        sm->lpre[nl] = run;
+        sm->n_light = nl;
+        sm->overflow = 0;
+      }
+      __syncthreads();
+      const uint32_t ltotal = sm->lpre[sm->n_light];
+      int32_t ldoc[kBmLight];
+      float lval[kBmLight];
+      int ltk[kBmLight];
+#pragma unroll
+      for (int u = 0; u < kBmLight; ++u) {
+        const uint32_t j = u * kBmThreads + tid;
+        ltk[u] = -1;
+        ldoc[u] = 0;
+        lval[u] = 0.f;
+        if (j < ltotal) {
+          int lo = 0, hi = sm->n_light;            // largest i with lpre[i] <= j
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (sm->lpre[mid] <= j) lo = mid; else hi = mid;
+          }
+          const int t = sm->ltok[lo];
+          const int64_t o = sm->offs[t][r] + (j - sm->lpre[lo]);
+          ltk[u] = t;
+          ldoc[u] = __ldg(p.indices + o);
+          lval[u] = __ldg(p.data + o);
+        }
+      }
+      float* acc = sm->acc - rs;                    // acc[doc] for docs of this range
+      for (int t = 0; t < T; ++t) {
+        const uint32_t n = cnt_of(t);
+        if (n == 0) continue;
+        if (sm->lstart[t] != 0xFFFFFFFFu) {
+#pragma unroll
+          for (int u = 0; u < kBmLight; ++u)
+            if (ltk[u] == t) acc[ldoc[u]] += lval[u];
+        } else {
+          // stream: 16-byte loads over the aligned middle, scalar head and tail.  Inside one token every
+          // doc occurs once, so the plain read-modify-write of different threads never collide.
+          const int64_t o0 = sm->offs[t][r];
+          const int32_t* ip = p.indices + o0;
+          const float* dp = p.data + o0;
+          const uint32_t head = min(n, static_cast<uint32_t>((4 - (o0 & 3)) & 3));
+          const uint32_t nvec = (n - head) >> 2;
+          if (tid < head) acc[__ldg(ip + tid)] += __ldg(dp + tid);
+          const int4* ip4 = reinterpret_cast<const int4*>(ip + head);
+          const float4* dp4 = reinterpret_cast<const float4*>(dp + head);
+          for (uint32_t base = 0; base < nvec; base += kBmThreads * 4) {
+            int4 d4[4];
+            float4 v4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t i = base + u * kBmThreads + tid;
+              if (i < nvec) { d4[u] = __ldg(ip4 + i); v4[u] = __ldg(dp4 + i); }
+              else { d4[u] = make_int4(-1, -1, -1, -1); v4[u] = make_float4(0.f, 0.f, 0.f, 0.f); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (d4[u].x >= 0) {
+                acc[d4[u].x] += v4[u].x;
+                acc[d4[u].y] += v4[u].y;
+                acc[d4[u].z] += v4[u].z;
+                acc[d4[u].w] += v4[u].w;
+              }
+            }
+          }
+          const uint32_t tail0 = head + (nvec << 2);
+          if (tail0 + tid < n) acc[__ldg(ip + tail0 + tid)] += __ldg(dp + tail0 + tid);
+        }
+        __syncthreads();    // token t fully applied before token t+1 touches the same docs
+      }
+
       if (p.dump != nullptr) {
-        for (int i = tid; i < tile_docs; i += kBmThreads) p.dump[tile_start + i] = sm->acc[i];
+        for (int i = tid; i < kBmRange; i += kBmThreads) {
+          if (i < range_docs) p.dump[rs + i] = sm->acc[i];
+          sm->acc[i] = 0.f;
+        }
       } else {
-        for (int s0 = 0; s0 < tile_docs; s0 += kBmScan) {
-          for (int i = s0 + tid; i < min(s0 + kBmScan, tile_docs); i += kBmThreads) {
-            const float v = sm->acc[i];
-            if (!p.all_positive || v > 0.f) {
-              const uint64_t key = make_key(v, static_cast<uint32_t>(tile_start + i));
-              if (key > sm->tau) skeys[atomicAdd(&sm->count, 1u)] = key;
+        // filter the range against the threshold; a full key buffer is compacted and the range rescanned
+        for (;;) {
+          const uint64_t tau = sm->tau;
+          const float tau_f = (tau == kKeyNone) ? -INFINITY : key_score(tau);
+          const float4* acc4 = reinterpret_cast<const float4*>(sm->acc);
+          for (int i4 = tid; i4 < kBmRange / 4; i4 += kBmThreads) {
+            const float4 v = acc4[i4];
+            const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+            if (mx >= tau_f && (!p.all_positive || mx > 0.f)) {
+              const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = i4 * 4 + e;
+                if (i < range_docs && vv[e] >= tau_f && (!p.all_positive || vv[e] > 0.f)) {
+                  const uint64_t key = make_key(vv[e], static_cast<uint32_t>(rs + i));
+                  if (key > tau) {
+                    const uint32_t pos = atomicAdd(&sm->count, 1u);
+                    if (pos < static_cast<uint32_t>(p.cap)) skeys[pos] = key;
+                    else sm->overflow = 1;
+                  }
+                }
+              }
             }
           }
           __syncthreads();
-          const uint32_t c = sm->count;
-          if (c + kBmScan > static_cast<uint32_t>(p.cap)) {
-            for (uint32_t i = c + tid; i < static_cast<uint32_t>(p.cap); i += kBmThreads) skeys[i] = 0ull;
-            block_bitonic_desc(skeys, p.cap);
-            if (tid == 0) { sm->count = p.keep; sm->tau = skeys[p.keep - 1]; }
+          const bool over = sm->overflow != 0;
+          const uint32_t c = min(sm->count, static_cast<uint32_t>(p.cap));
+          __syncthreads();
+          if (!over && c + 256 <= static_cast<uint32_t>(p.cap)) break;
+          // compact to the k' best (every stored key is a valid candidate, so the k'-th stored key is a valid
+          // lower bound for the threshold)
+          for (uint32_t i = c + tid; i < static_cast<uint32_t>(p.cap); i += kBmThreads) skeys[i] = 0ull;
+          block_bitonic_desc(skeys, p.cap);
+          const uint32_t kept = min(c, static_cast<uint32_t>(p.keep));
+          if (!over) {
+            if (tid == 0) {
+              sm->count = kept;
+              if (c >= static_cast<uint32_t>(p.keep)) {
+                sm->tau = skeys[p.keep - 1];
+                if (p.qtau != nullptr) atomicMax(p.qtau + q, static_cast<unsigned long long>(sm->tau));
+              }
+            }
             __syncthreads();
+            break;
           }
+          // overflow: some keys of this range were dropped.  Raise the threshold to just below the k'-th
+          // stored key, drop the survivors that belong to this range (the rescan re-admits them) and rescan.
+          uint64_t mine[4];                       // kept <= 1024 = 4 per thread
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t i = tid + j * kBmThreads;
+            mine[j] = (i < kept) ? skeys[i] : 0ull;
+          }
+          const uint64_t new_tau = (c >= static_cast<uint32_t>(p.keep)) ? skeys[p.keep - 1] - 1ull : sm->tau;
+          __syncthreads();
+          if (tid == 0) {
+            sm->count = 0;
+            sm->tau = new_tau;
+            sm->overflow = 0;
+            if (p.qtau != nullptr) atomicMax(p.qtau + q, static_cast<unsigned long long>(new_tau));
+          }
+          __syncthreads();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (mine[j] != 0ull) {
+              const int64_t id = key_id(mine[j]);
+              if (id < rs || id >= re) skeys[atomicAdd(&sm->count, 1u)] = mine[j];
+            }
+          }
+          __syncthreads();
         }
+        float4* z4 = reinterpret_cast<float4*>(sm->acc);
+        for (int i4 = tid; i4 < kBmRange / 4; i4 += kBmThreads) z4[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      tile_start = tile_end;
+      __syncthreads();
     }
 
     if (p.dump == nullptr) {
       __syncthreads();
       const uint32_t c = sm->count;
-      for (uint32_t i = c + tid; i < static_cast<uint32_t>(p.cap); i += kBmThreads) skeys[i] = 0ull;
-      block_bitonic_desc(skeys, p.cap);
-      const uint32_t n = min(c, static_cast<uint32_t>(p.keep));
+      uint32_t n = c;
+      if (c > static_cast<uint32_t>(p.keep)) {         // more than k' survivors: keep the best k'
+        for (uint32_t i = c + tid; i < static_cast<uint32_t>(p.cap); i += kBmThreads) skeys[i] = 0ull;
+        block_bitonic_desc(skeys, p.cap);
+        n = p.keep;
+        if (tid == 0 && p.qtau != nullptr) atomicMax(p.qtau + q, static_cast<unsigned long long>(skeys[p.keep - 1]));
+      }
       const size_t slot = static_cast<size_t>(seg) * p.nq_pad + q;
       for (uint32_t i = tid; i < n; i += kBmThreads) p.cand[slot * p.keep + i] = skeys[i];
       if (tid == 0) p.cand_count[slot] = n;

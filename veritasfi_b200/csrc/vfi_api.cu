@@ -149,6 +149,59 @@ int device_props(int device, cudaDeviceProp* prop) {
   return VFI_OK;
 }
 
+// the streaming scorer is instantiated per query count (1..8) so the accumulators stay in registers
+template <typename RowT, int NQ>
+void gemv_launch_one(int grid, size_t smem, cudaStream_t st, const RowT* rows, int64_t pitch, int dp, int64_t n, const float* q,
+                     int keep, int cap_s, uint64_t* cand, uint32_t* cnt, int nq_pad, int cand_cap) {
+  vfi::gemv_topk_kernel<RowT, NQ><<<grid, vfi::kGemvThreads, smem, st>>>(rows, pitch, dp, n, q, keep, cap_s, cand, cnt, nq_pad, cand_cap);
+}
+template <typename RowT>
+void gemv_launch(int nq, int grid, size_t smem, cudaStream_t st, const RowT* rows, int64_t pitch, int dp, int64_t n, const float* q,
+                 int keep, int cap_s, uint64_t* cand, uint32_t* cnt, int nq_pad, int cand_cap) {
+  switch (nq) {
+    case 1: gemv_launch_one<RowT, 1>(grid, smem, st, rows, pitch, dp, n, q, keep, cap_s, cand, cnt, nq_pad, cand_cap); break;
+    case 2: gemv_launch_one<RowT, 2>(grid, smem, st, rows, pitch, dp, n, q, keep, cap_s, cand, cnt, nq_pad, cand_cap); break;
+    case 3: gemv_launch_one<RowT, 3>(grid, smem, st, rows, pitch, dp, n, q, keep, cap_s, cand, cnt, nq_pad, cand_cap); break;
+    case 4: gemv_launch_one<RowT, 4>(grid, smem, st, rows, pitch, dp, n, q, keep, cap_s, cand, cnt, nq_pad, cand_cap); break;
+    case 5: gemv_launch_one<RowT, 5>(grid, smem, st, rows, pitch, dp, n, q, keep, cap_s, cand, cnt, nq_pad, cand_cap); break;
+    case 6: gemv_launch_one<RowT, 6>(grid, smem, st, rows, pitch, dp, n, q, keep, cap_s, cand, cnt, nq_pad, cand_cap); break;
+    case 7: gemv_launch_one<RowT, 7>(grid, smem, st, rows, pitch, dp, n, q, keep, cap_s, cand, cnt, nq_pad, cand_cap); break;
+    default: gemv_launch_one<RowT, 8>(grid, smem, st, rows, pitch, dp, n, q, keep, cap_s, cand, cnt, nq_pad, cand_cap); break;
+  }
+}
+template <typename RowT, int NQ>
+int gemv_occ_one(size_t smem) {
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vfi::gemv_topk_kernel<RowT, NQ>, vfi::kGemvThreads, smem) != cudaSuccess) {
+    cudaGetLastError();
+    occ = 1;
+  }
+  return occ < 1 ? 1 : occ;
+}
+template <typename RowT>
+int gemv_occupancy(int nq, size_t smem) {
+  switch (nq) {
+    case 1: return gemv_occ_one<RowT, 1>(smem);
+    case 2: return gemv_occ_one<RowT, 2>(smem);
+    case 3: return gemv_occ_one<RowT, 3>(smem);
+    case 4: return gemv_occ_one<RowT, 4>(smem);
+    case 5: return gemv_occ_one<RowT, 5>(smem);
+    case 6: return gemv_occ_one<RowT, 6>(smem);
+    case 7: return gemv_occ_one<RowT, 7>(smem);
+    default: return gemv_occ_one<RowT, 8>(smem);
+  }
+}
+template <typename RowT, int NQ>
+void gemv_attr_one() {
+  cudaFuncSetAttribute(vfi::gemv_topk_kernel<RowT, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+}
+void gemv_set_smem_attr() {
+  gemv_attr_one<uint16_t, 1>(); gemv_attr_one<uint16_t, 2>(); gemv_attr_one<uint16_t, 3>(); gemv_attr_one<uint16_t, 4>();
+  gemv_attr_one<uint16_t, 5>(); gemv_attr_one<uint16_t, 6>(); gemv_attr_one<uint16_t, 7>(); gemv_attr_one<uint16_t, 8>();
+  gemv_attr_one<float, 1>(); gemv_attr_one<float, 2>(); gemv_attr_one<float, 3>(); gemv_attr_one<float, 4>();
+  gemv_attr_one<float, 5>(); gemv_attr_one<float, 6>(); gemv_attr_one<float, 7>(); gemv_attr_one<float, 8>();
+}
+
 constexpr int kMaxQueriesPerLaunch = 1024;
 constexpr int kExhaustiveRows = 4096;   // shards this small skip the tensor-core pass
 constexpr int kFusedMaxKeep = 1024;
@@ -220,8 +273,7 @@ int vfi_index_create(int d, int store_dtype, int device, vfi_index_t** out) {
   cudaEventCreate(&idx->ev1);
   cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kDenseSmemBytes);
   cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kDenseSmemBytes);
-  cudaFuncSetAttribute(vfi::gemv_topk_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  cudaFuncSetAttribute(vfi::gemv_topk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  gemv_set_smem_attr();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return bail(fail(VFI_ERR_CUDA, std::string("kernel attribute setup: ") + cudaGetErrorString(e)));
   *out = idx;
@@ -401,6 +453,12 @@ int vfi_index_reconstruct(vfi_index_t* idx, int64_t i, float* out, int mem) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+// rows must fit the register-resident pieces of the streaming scorer
+bool gemv_ok(const vfi_index* idx) {
+  const int bytes = idx->dp * (idx->store == VFI_STORE_F32 ? 4 : 2);
+  return bytes <= vfi::kGemvMaxVec * 32 * 16;
+}
+
 int prep_queries(vfi_index* idx, const float* q_dev, int nq, cudaStream_t st) {
   VFI_TRY(idx->w_qcanon.ensure(static_cast<size_t>(nq) * idx->dp * 4));
   VFI_TRY(idx->w_qg.ensure(static_cast<size_t>(nq) * idx->kp * 2));
@@ -521,12 +579,12 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
   int path = static_cast<int>(idx->opt_force_path);
   if (path == 0) {
     if (n <= kExhaustiveRows || keep >= n) path = 1;
-    else if (nq <= vfi::kGemvMaxQ && keep <= kGemvMaxKeep) path = 3;
+    else if (nq <= vfi::kGemvMaxQ && keep <= kGemvMaxKeep && gemv_ok(idx)) path = 3;
     else if (keep <= kFusedMaxKeep) path = 2;
     else path = 1;
   }
   if (path == 2 && (keep > kFusedMaxKeep || n == 0)) path = 1;
-  if (path == 3 && (nq > vfi::kGemvMaxQ || keep > kGemvMaxKeep || n == 0)) path = 1;
+  if (path == 3 && (nq > vfi::kGemvMaxQ || keep > kGemvMaxKeep || n == 0 || !gemv_ok(idx))) path = (keep <= kFusedMaxKeep && n > 0) ? 2 : 1;
   idx->stats.last_path = path;
   idx->stats.last_overfetch = keep;
   if (path == 1) return exhaustive_pass(idx, nullptr, nq, k, out_scores, out_ids, st);
@@ -542,7 +600,7 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
     const int m = 8;
     const int64_t rs = 2 * static_cast<int64_t>(keep) + 1;
     const int64_t rr = n / rs;
-    if (rr >= 64 * m || idx->opt_tau_hint == 2) {
+    if (rr >= 4 * m || idx->opt_tau_hint == 2) {
       const int64_t ld = ceil_div(rr, vfi::kBN) * vfi::kBN;
       const int64_t nq_pad_s = ceil_div(nq, vfi::kBM) * vfi::kBM;
       VFI_TRY(idx->w_dbg.ensure(static_cast<size_t>(nq_pad_s) * ld * 4));
@@ -564,7 +622,7 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
     while (cap_s < keep + vfi::kGemvRowsPerRound) cap_s <<= 1;
     const size_t smem = ((static_cast<size_t>(nq) * idx->dp * 4 + 15) & ~size_t(15)) + static_cast<size_t>(nq) * cap_s * 8 + 256;
     if (smem > 160 * 1024) return fail(VFI_ERR_UNSUPPORTED, "streaming scorer: query block does not fit shared memory");
-    const int ctas_per_sm = std::max<int>(1, std::min<int>(3, static_cast<int>((200 * 1024) / smem)));
+    const int ctas_per_sm = (idx->store == VFI_STORE_F32) ? gemv_occupancy<float>(nq, smem) : gemv_occupancy<uint16_t>(nq, smem);
     n_groups = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(idx->num_sms) * ctas_per_sm,
                                                   ceil_div(n, vfi::kGemvRowsPerRound)));
     nq_pad = nq;
@@ -574,13 +632,11 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
     const bool prof = idx->opt_profile != 0;
     if (prof) cudaEventRecord(idx->ev0, st);
     if (idx->store == VFI_STORE_F32)
-      vfi::gemv_topk_kernel<float><<<n_groups, vfi::kGemvThreads, smem, st>>>(
-          idx->master, idx->dp, idx->dp, n, idx->w_qcanon.as<float>(), nq, keep, cap_s, idx->w_cand.as<uint64_t>(),
-          idx->w_cand_count.as<uint32_t>(), nq_pad, cap);
+      gemv_launch<float>(nq, n_groups, smem, st, idx->master, idx->dp, idx->dp, n, idx->w_qcanon.as<float>(), keep, cap_s,
+                         idx->w_cand.as<uint64_t>(), idx->w_cand_count.as<uint32_t>(), nq_pad, cap);
     else
-      vfi::gemv_topk_kernel<uint16_t><<<n_groups, vfi::kGemvThreads, smem, st>>>(
-          idx->g, idx->kp, idx->dp, n, idx->w_qcanon.as<float>(), nq, keep, cap_s, idx->w_cand.as<uint64_t>(),
-          idx->w_cand_count.as<uint32_t>(), nq_pad, cap);
+      gemv_launch<uint16_t>(nq, n_groups, smem, st, idx->g, idx->kp, idx->dp, n, idx->w_qcanon.as<float>(), keep, cap_s,
+                            idx->w_cand.as<uint64_t>(), idx->w_cand_count.as<uint32_t>(), nq_pad, cap);
     LAUNCHED();
     if (prof) cudaEventRecord(idx->ev1, st);
     VFI_CUDA(cudaGetLastError());
@@ -1032,11 +1088,21 @@ int vfi_bm25_search(vfi_bm25_t* b, const int32_t* q_tokens, const int64_t* q_ind
   int cap = 1;
   while (cap < keep + vfi::kBmScan) cap <<= 1;
   const size_t smem = ((sizeof(vfi::Bm25Smem) + 15) & ~size_t(15)) + static_cast<size_t>(cap) * 8;
-  const int n_ctas = b->num_sms * 2;
-  const int64_t n_tiles = std::max<int64_t>(1, ceil_div(b->n_docs, vfi::kBmTile));
-  int64_t n_seg = std::min<int64_t>(std::min<int64_t>(n_tiles, 1024), std::max<int64_t>(1, ceil_div(static_cast<int64_t>(8) * n_ctas, nq)));
-  const int64_t seg_docs = ceil_div(n_tiles, n_seg) * vfi::kBmTile;
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vfi::bm25_kernel, vfi::kBmThreads, smem) != cudaSuccess) {
+    cudaGetLastError();
+    occ = 1;
+  }
+  const int n_ctas = b->num_sms * std::max(1, occ);
+  const int64_t n_ranges = std::max<int64_t>(1, ceil_div(b->n_docs, vfi::kBmRange));
+  // about 8 work items per resident CTA (the atomic work queue balances heavy and light queries),
+  // segments of at most kBmMaxRanges ranges
+  int64_t n_seg = std::max<int64_t>(ceil_div(n_ranges, vfi::kBmMaxRanges),
+                                    std::min<int64_t>(n_ranges, ceil_div(static_cast<int64_t>(8) * n_ctas, nq)));
+  n_seg = std::min<int64_t>(n_seg, n_ranges);
+  const int64_t seg_docs = ceil_div(n_ranges, n_seg) * vfi::kBmRange;
   n_seg = std::max<int64_t>(1, ceil_div(b->n_docs, seg_docs));
+  if (n_seg > 1024) return fail(VFI_ERR_UNSUPPORTED, "bm25 shard too large: more than 1024 doc segments (shard the postings)");
   VFI_TRY(b->w_tok.ensure(std::max<size_t>(16, static_cast<size_t>(n_tok) * 4)));
   VFI_TRY(b->w_qptr.ensure(static_cast<size_t>(nq + 1) * 8));
   VFI_TRY(b->w_cand.ensure(static_cast<size_t>(n_seg) * nq * keep * 8));
@@ -1046,10 +1112,10 @@ int vfi_bm25_search(vfi_bm25_t* b, const int32_t* q_tokens, const int64_t* q_ind
   VFI_TRY(b->w_bound.ensure(static_cast<size_t>(nq) * 4));
   VFI_TRY(b->w_out_scores.ensure(static_cast<size_t>(nq) * k * 4));
   VFI_TRY(b->w_out_ids.ensure(static_cast<size_t>(nq) * k * 8));
-  VFI_TRY(b->w_ctr.ensure(16));
+  VFI_TRY(b->w_ctr.ensure(16 + static_cast<size_t>(nq) * 8));
   if (n_tok > 0) VFI_CUDA(cudaMemcpyAsync(b->w_tok.p, q_tokens, static_cast<size_t>(n_tok) * 4, cudaMemcpyHostToDevice, st));
   VFI_CUDA(cudaMemcpyAsync(b->w_qptr.p, q_indptr, static_cast<size_t>(nq + 1) * 8, cudaMemcpyHostToDevice, st));
-  VFI_CUDA(cudaMemsetAsync(b->w_ctr.p, 0, 16, st));
+  VFI_CUDA(cudaMemsetAsync(b->w_ctr.p, 0, 16 + static_cast<size_t>(nq) * 8, st));
   VFI_CUDA(cudaMemsetAsync(b->w_cand_count.p, 0, static_cast<size_t>(n_seg) * nq * 4, st));
   vfi::Bm25Params p{};
   p.indptr = b->indptr;
@@ -1068,6 +1134,7 @@ int vfi_bm25_search(vfi_bm25_t* b, const int32_t* q_tokens, const int64_t* q_ind
   p.cand = b->w_cand.as<uint64_t>();
   p.cand_count = b->w_cand_count.as<uint32_t>();
   p.work_counter = b->w_ctr.as<uint32_t>();
+  p.qtau = reinterpret_cast<unsigned long long*>(b->w_ctr.as<uint8_t>() + 16);
   p.dump = nullptr;
   const int grid = static_cast<int>(std::min<int64_t>(n_ctas, nq * n_seg));
   if (b->profile) cudaEventRecord(b->ev0, st);
@@ -1114,12 +1181,17 @@ int vfi_bm25_score_all(vfi_bm25_t* b, const int32_t* q_tokens, int64_t n_tokens,
   int64_t bytes = 0;
   VFI_TRY(bm25_validate_tokens(b, q_tokens, qptr, 1, &bytes));
   if (b->n_docs == 0) return VFI_OK;
-  int cap = 2048;
+  const int cap = 2048;
   const size_t smem = ((sizeof(vfi::Bm25Smem) + 15) & ~size_t(15)) + static_cast<size_t>(cap) * 8;
-  const int n_ctas = b->num_sms * 2;
-  const int64_t n_tiles = std::max<int64_t>(1, ceil_div(b->n_docs, vfi::kBmTile));
-  int64_t n_seg = std::min<int64_t>(n_tiles, n_ctas);
-  const int64_t seg_docs = ceil_div(n_tiles, n_seg) * vfi::kBmTile;
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vfi::bm25_kernel, vfi::kBmThreads, smem) != cudaSuccess) {
+    cudaGetLastError();
+    occ = 1;
+  }
+  const int n_ctas = b->num_sms * std::max(1, occ);
+  const int64_t n_ranges = std::max<int64_t>(1, ceil_div(b->n_docs, vfi::kBmRange));
+  int64_t n_seg = std::max<int64_t>(ceil_div(n_ranges, vfi::kBmMaxRanges), std::min<int64_t>(n_ranges, n_ctas));
+  const int64_t seg_docs = ceil_div(n_ranges, n_seg) * vfi::kBmRange;
   n_seg = std::max<int64_t>(1, ceil_div(b->n_docs, seg_docs));
   VFI_TRY(b->w_tok.ensure(std::max<size_t>(16, static_cast<size_t>(n_tokens) * 4)));
   VFI_TRY(b->w_qptr.ensure(16));
@@ -1149,6 +1221,7 @@ int vfi_bm25_score_all(vfi_bm25_t* b, const int32_t* q_tokens, int64_t n_tokens,
   p.cand = nullptr;
   p.cand_count = nullptr;
   p.work_counter = b->w_ctr.as<uint32_t>();
+  p.qtau = nullptr;
   p.dump = dump;
   vfi::bm25_kernel<<<static_cast<int>(std::min<int64_t>(n_ctas, n_seg)), vfi::kBmThreads, smem, st>>>(p);
   LAUNCHED();
