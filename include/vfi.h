@@ -97,7 +97,8 @@ enum {
   VFI_OPT_FORCE_PATH = 2,    /* 0 auto, 1 exhaustive exact, 2 fused tcgen05, 3 streaming GEMV */
   VFI_OPT_PROFILE = 3,       /* 1: bracket the dominant kernel with CUDA events */
   VFI_OPT_TAU_HINT = 4,      /* 1: estimate a per-query admission threshold from a row sample (2: debug, admit nothing) */
-  VFI_OPT_NUM_CTAS = 5       /* 0 = one CTA per SM */
+  VFI_OPT_NUM_CTAS = 5,      /* 0 = one CTA per SM */
+  VFI_OPT_CLUSTER = 6        /* CTAs per thread-block cluster sharing corpus tiles by TMA multicast: 0/1 off, 2, 4, 8 */
 };
 int vfi_index_set_option(vfi_index_t* idx, int opt, int64_t value);
 

@@ -85,6 +85,24 @@ def test_dense_search_matches_oracle(torch_cuda, n, d, nq, k, store, path):
     idx.close()
 
 
+def test_reference_online_depth_k2048(torch_cuda):
+    """The reference's own online call: depth 2048 for 1-4 query strings (ensembleRetriever.py:64-66)."""
+    from oracle import flat_ip
+    from veritasfi_b200 import faiss_compat
+    xb, xq = _world(30000, 96, 4, 12, False)
+    index = faiss_compat.IndexFlatIP(96)
+    index.add(xb)
+    D, I = index.search(xq, 2048)
+    D0, I0 = flat_ip.search(xq, xb, 2048)
+    assert (I == I0).all() and (D == D0).all()
+    xb2 = xb[:1500].copy()                       # corpus smaller than the depth: padded like faiss
+    index2 = faiss_compat.IndexFlatIP(96)
+    index2.add(xb2)
+    D, I = index2.search(xq, 2048)
+    D0, I0 = flat_ip.search_exhaustive(xq, xb2, 2048)
+    assert (I == I0).all() and (D == D0).all() and (I[:, 1500:] == -1).all()
+
+
 def test_admission_hint_does_not_change_results(torch_cuda):
     torch = torch_cuda
     from oracle import flat_ip
@@ -293,6 +311,15 @@ def test_bm25_general_impacts_and_doc_shards():
     mi, ms = osh.merge(np.stack(parts_s), np.stack(parts_i), 30)
     I0, S0 = obm.retrieve(indptr, indices, data, qs, n_docs, 30)
     assert (mi == I0).all() and (ms == S0).all()
+
+
+def test_bm25_rejects_malformed_postings():
+    from veritasfi_b200 import _native as N
+    from veritasfi_b200.bm25_compat import GpuPostings
+    with pytest.raises(N.VfiError):
+        GpuPostings(np.array([0, 2]), np.array([3, 1], np.int32), np.ones(2, np.float32), 5)      # not ascending
+    with pytest.raises(N.VfiError):
+        GpuPostings(np.array([0, 1]), np.array([9], np.int32), np.ones(1, np.float32), 5)         # out of range
 
 
 def test_bm25_facade_retrieve_like_bm25s(tmp_path):

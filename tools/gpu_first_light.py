@@ -172,6 +172,51 @@ def fuse():
 
 
 @stage
+def cluster():
+    """TMA-multicast clusters: same results, timing per cluster size."""
+    import torch
+    from veritasfi_b200 import synth, _native as N
+    from veritasfi_b200.dense import DenseIndex
+    dev = torch.device("cuda", 0)
+    for (n, d, nq, k) in [(1_000_000, 1024, 256, 100), (4_000_000, 1024, 1024, 100)]:
+        xb = synth.dense_corpus_torch(n, d, 1235, dev)
+        idx = DenseIndex(d, store="bf16")
+        idx.add(xb)
+        del xb
+        q = synth.dense_queries_torch(nq, d, 1235, dev)
+        idx.set_option(N.OPT_PROFILE, 1)
+        idx.set_option(N.OPT_TAU_HINT, 1)
+        ref = None
+        for c in (1, 2, 4, 8):
+            if c > max(1, nq // 128):
+                continue
+            idx.set_option(N.OPT_CLUSTER, c)
+            try:
+                for _ in range(3):
+                    I, D = idx.search_batch(q, k)
+                torch.cuda.synchronize()
+            except Exception as e:
+                print(f"[cluster n={n} nq={nq} C={c}] FAILED: {e}", flush=True)
+                break
+            idx.stats(reset=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(8):
+                I, D = idx.search_batch(q, k)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 8
+            st = idx.stats()
+            kms = st.fused_ms_total / max(1, st.fused_ms_samples)
+            tf = 2.0 * nq * n * d / (kms * 1e-3) / 1e12
+            if ref is None:
+                ref = (I.clone(), D.clone())
+            same = bool((I == ref[0]).all() and (D == ref[1]).all())
+            print(f"[cluster n={n} nq={nq} C={c}] step={ms:.3f} ms fused_kernel={kms:.3f} ms ({tf:.0f} TFLOP/s) same_as_C1={same} retried={st.retried_queries}", flush=True)
+        idx.close()
+
+
+@stage
 def perf():
     import torch
     from veritasfi_b200 import synth, _native as N

@@ -261,6 +261,97 @@ __global__ void __launch_bounds__(256) tau_from_scores_kernel(const float* __res
 //   cand_keys == nullptr : rows are all_lo .. all_lo+all_n of the shard       (exhaustive)
 // Output keys2[q][i] = make_key(exact fp32 score, id); pairs beyond the count get kKeyNone.
 // ------------------------------------------------------------------------------------------
+constexpr int kCanonWords = 64;                 // 32-bit words per staged row chunk (256 B)
+constexpr int kCanonPitch = kCanonWords + 1;    // conflict-free row walk
+template <typename RowT>
+struct CanonCfg {
+  static constexpr int kElems = kCanonWords * 4 / static_cast<int>(sizeof(RowT));  // 128 bf16 or 64 fp32 per chunk
+};
+
+// Canonical scores of 32 rows against one query: lane l owns row `id` (valid or not).  my_tile: 32*kCanonPitch
+// words, my_qs: CanonCfg<RowT>::kElems doubles, both private to the calling warp.  All 32 lanes must call.
+template <typename RowT>
+__device__ __forceinline__ float canon_dot_warp(const RowT* __restrict__ rows, int64_t row_pitch, int dp,
+                                                const float* __restrict__ qv, uint32_t id, bool valid,
+                                                uint32_t* my_tile, double* my_qs, uint32_t lane) {
+  constexpr int kElems = CanonCfg<RowT>::kElems;
+  constexpr int kLoads = 16;                                   // warp loads per chunk (2 rows x 16 uint4 each)
+  // this lane loads the 16-byte piece (lane & 15) of rows (lane >> 4) + 2*it, it = 0..15
+  const int v = lane & 15;
+  const uint8_t* src[kLoads];
+#pragma unroll
+  for (int it = 0; it < kLoads; ++it) {
+    const int r = it * 2 + (lane >> 4);
+    const uint32_t rid = __shfl_sync(0xFFFFFFFFu, id, r);
+    const bool rvalid = __shfl_sync(0xFFFFFFFFu, valid ? 1 : 0, r) != 0;
+    src[it] = rvalid ? reinterpret_cast<const uint8_t*>(rows + static_cast<int64_t>(rid) * row_pitch) + v * 16 : nullptr;
+  }
+  const int vec_elems = 16 / static_cast<int>(sizeof(RowT));
+  double acc = 0.0;
+  uint4 pre[kLoads];
+  auto fetch = [&](int c0) {
+#pragma unroll
+    for (int it = 0; it < kLoads; ++it) {
+      pre[it] = make_uint4(0, 0, 0, 0);
+      if (src[it] != nullptr && c0 + v * vec_elems < dp)
+        pre[it] = ptx::ld_nc_u4(src[it] + static_cast<size_t>(c0) * sizeof(RowT));
+    }
+  };
+  fetch(0);
+  for (int c0 = 0; c0 < dp; c0 += kElems) {
+#pragma unroll
+    for (int it = 0; it < kLoads; ++it) {
+      uint32_t* dst = my_tile + (it * 2 + (lane >> 4)) * kCanonPitch + v * 4;
+      dst[0] = pre[it].x; dst[1] = pre[it].y; dst[2] = pre[it].z; dst[3] = pre[it].w;
+    }
+    for (int e = lane; e < kElems; e += 32) my_qs[e] = (c0 + e < dp) ? static_cast<double>(qv[c0 + e]) : 0.0;
+    __syncwarp();
+    if (c0 + kElems < dp) fetch(c0 + kElems);          // next chunk in flight while this one is summed
+    const uint32_t* mine = my_tile + lane * kCanonPitch;
+    // batches of 8 words: all shared loads and widenings first, then the dependent fp64 chain
+#pragma unroll 1
+    for (int w0 = 0; w0 < kCanonWords; w0 += 8) {
+      uint32_t u[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] = mine[w0 + i];
+      uint32_t odd = 0;
+      if (sizeof(RowT) == 2) {
+        double xd[16], qd[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) qd[i] = my_qs[2 * w0 + i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xd[2 * i] = widen_f32_bits(u[i] << 16, odd);
+          xd[2 * i + 1] = widen_f32_bits(u[i] & 0xFFFF0000u, odd);
+        }
+        if (odd) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            xd[2 * i] = static_cast<double>(__uint_as_float(u[i] << 16));
+            xd[2 * i + 1] = static_cast<double>(__uint_as_float(u[i] & 0xFFFF0000u));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc = fma(qd[i], xd[i], acc);
+      } else {
+        double xd[8], qd[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qd[i] = my_qs[w0 + i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xd[i] = widen_f32_bits(u[i], odd);
+        if (odd) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xd[i] = static_cast<double>(__uint_as_float(u[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fma(qd[i], xd[i], acc);
+      }
+    }
+    __syncwarp();
+  }
+  return static_cast<float>(acc);
+}
+
 template <typename RowT>
 __global__ void __launch_bounds__(128) canon_score_kernel(
     const RowT* __restrict__ rows, int64_t row_pitch, int dp, const float* __restrict__ qcanon,
@@ -268,12 +359,8 @@ __global__ void __launch_bounds__(128) canon_score_kernel(
     const uint32_t* __restrict__ n_cand, int keep, int64_t all_n, uint64_t* __restrict__ keys2,
     int64_t keys2_pitch, uint32_t* __restrict__ max_err_bits) {
   constexpr int kWarps = 4;
-  constexpr int kWords = 64;                                   // 32-bit words per row chunk (256 B)
-  constexpr int kElems = kWords * 4 / static_cast<int>(sizeof(RowT));  // 128 bf16 or 64 fp32 per chunk
-  constexpr int kPitch = kWords + 1;                           // conflict-free row walk
-  constexpr int kLoads = 16;                                   // warp loads per chunk (2 rows x 16 uint4 each)
-  __shared__ uint32_t tile[kWarps][32 * kPitch];
-  __shared__ double qs[kWarps][kElems];   // the query chunk, already widened to fp64
+  __shared__ uint32_t tile[kWarps][32 * kCanonPitch];
+  __shared__ double qs[kWarps][CanonCfg<RowT>::kElems];   // the query chunk, already widened to fp64
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qslot = blockIdx.y;                       // index into the selected-query list
   const int q = (qsel != nullptr) ? qsel[qslot] : qslot;
@@ -295,82 +382,8 @@ __global__ void __launch_bounds__(128) canon_score_kernel(
       id = static_cast<uint32_t>(slot);
     }
   }
-  // this lane loads the 16-byte piece (lane & 15) of rows (lane >> 4) + 2*it, it = 0..15
-  const int v = lane & 15;
-  const uint8_t* src[kLoads];
-#pragma unroll
-  for (int it = 0; it < kLoads; ++it) {
-    const int r = it * 2 + (lane >> 4);
-    const uint32_t rid = __shfl_sync(0xFFFFFFFFu, id, r);
-    const bool rvalid = __shfl_sync(0xFFFFFFFFu, valid ? 1 : 0, r) != 0;
-    src[it] = rvalid ? reinterpret_cast<const uint8_t*>(rows + static_cast<int64_t>(rid) * row_pitch) + v * 16 : nullptr;
-  }
-  const int vec_elems = 16 / static_cast<int>(sizeof(RowT));
-  const float* qv = qcanon + static_cast<int64_t>(q) * dp;
-  double acc = 0.0;
-  uint32_t* my_tile = tile[warp];
-  uint4 pre[kLoads];
-  auto fetch = [&](int c0) {
-#pragma unroll
-    for (int it = 0; it < kLoads; ++it) {
-      pre[it] = make_uint4(0, 0, 0, 0);
-      if (src[it] != nullptr && c0 + v * vec_elems < dp)
-        pre[it] = ptx::ld_nc_u4(src[it] + static_cast<size_t>(c0) * sizeof(RowT));
-    }
-  };
-  fetch(0);
-  for (int c0 = 0; c0 < dp; c0 += kElems) {
-#pragma unroll
-    for (int it = 0; it < kLoads; ++it) {
-      uint32_t* dst = my_tile + (it * 2 + (lane >> 4)) * kPitch + v * 4;
-      dst[0] = pre[it].x; dst[1] = pre[it].y; dst[2] = pre[it].z; dst[3] = pre[it].w;
-    }
-    for (int e = lane; e < kElems; e += 32) qs[warp][e] = (c0 + e < dp) ? static_cast<double>(qv[c0 + e]) : 0.0;
-    __syncwarp();
-    if (c0 + kElems < dp) fetch(c0 + kElems);          // next chunk in flight while this one is summed
-    const uint32_t* mine = my_tile + lane * kPitch;
-    // batches of 8 words: all shared loads and widenings first, then the dependent fp64 chain
-#pragma unroll 1
-    for (int w0 = 0; w0 < kWords; w0 += 8) {
-      uint32_t u[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) u[i] = mine[w0 + i];
-      uint32_t odd = 0;
-      if (sizeof(RowT) == 2) {
-        double xd[16], qd[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) qd[i] = qs[warp][2 * w0 + i];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          xd[2 * i] = widen_f32_bits(u[i] << 16, odd);
-          xd[2 * i + 1] = widen_f32_bits(u[i] & 0xFFFF0000u, odd);
-        }
-        if (odd) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            xd[2 * i] = static_cast<double>(__uint_as_float(u[i] << 16));
-            xd[2 * i + 1] = static_cast<double>(__uint_as_float(u[i] & 0xFFFF0000u));
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc = fma(qd[i], xd[i], acc);
-      } else {
-        double xd[8], qd[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) qd[i] = qs[warp][w0 + i];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xd[i] = widen_f32_bits(u[i], odd);
-        if (odd) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) xd[i] = static_cast<double>(__uint_as_float(u[i]));
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fma(qd[i], xd[i], acc);
-      }
-    }
-    __syncwarp();
-  }
-  const float s = static_cast<float>(acc);
+  const float s = canon_dot_warp<RowT>(rows, row_pitch, dp, qcanon + static_cast<int64_t>(q) * dp, id, valid, tile[warp],
+                                       qs[warp], lane);
   if (slot < slots) {
     keys2[static_cast<int64_t>(qslot) * keys2_pitch + slot] = valid ? make_key(s, id) : kKeyNone;
   }
@@ -427,6 +440,94 @@ __global__ void __launch_bounds__(256) finalize_kernel(
       out_ids[static_cast<int64_t>(q) * k + i] = has ? static_cast<int64_t>(key_id(key)) + id_offset : -1;
     }
   } else if (threadIdx.x == 0) {
+    flagged[atomicAdd(n_flagged, 1)] = q;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1c+K2 fused (k' <= 256): one CTA per query does the whole tail of a search — union of the group
+// buffers, k' best by tensor-core score, canonical rescoring (warps 0-3, 32 candidates each per round),
+// final order, certificate, output.  Saves two launches and the round trips through global memory.
+// ------------------------------------------------------------------------------------------
+struct TailSmem {
+  SelectSmem sel;
+  uint32_t pref[1025];
+  uint32_t tile[4][32 * kCanonPitch];
+  double qs[4][128];
+};
+
+template <typename RowT>
+__global__ void __launch_bounds__(256, 2) select_rescore_kernel(
+    const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, int n_groups, int nq_pad, int cap, int keep,
+    const float* __restrict__ tau_init, const RowT* __restrict__ rows, int64_t row_pitch, int dp,
+    const float* __restrict__ qcanon, int k, int64_t id_offset, const float* __restrict__ eps,
+    float* __restrict__ out_scores, int64_t* __restrict__ out_ids, int* __restrict__ flagged, int* __restrict__ n_flagged,
+    uint32_t* __restrict__ max_err_bits) {
+  extern __shared__ uint8_t smem_raw[];
+  TailSmem* ts = reinterpret_cast<TailSmem*>(smem_raw);
+  SelectSmem* sm = &ts->sel;
+  const int q = blockIdx.x;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int g = tid; g < n_groups; g += blockDim.x)
+    ts->pref[g + 1] = min(cnt[static_cast<size_t>(g) * nq_pad + q], static_cast<uint32_t>(cap));
+  if (tid == 0) ts->pref[0] = 0;
+  __syncthreads();
+  if (tid < 32) {
+    uint32_t carry = 0;
+    for (int base = 0; base < n_groups; base += 32) {
+      const int g = base + tid;
+      uint32_t v = (g < n_groups) ? ts->pref[g + 1] : 0u;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (static_cast<int>(tid) >= o) v += t;
+      }
+      if (g < n_groups) ts->pref[g + 1] = v + carry;
+      carry += __shfl_sync(0xFFFFFFFFu, v, 31);
+    }
+  }
+  __syncthreads();
+  const uint32_t total = ts->pref[n_groups];
+  GroupBufSrc src{cand, ts->pref, n_groups, nq_pad, cap, q};
+  const uint32_t n = block_topk(src, total, static_cast<uint32_t>(keep), sm);   // sm->keys[0..n) sorted by tensor-core score
+  float bound;
+  if (total >= static_cast<uint32_t>(keep)) bound = key_score(sm->keys[keep - 1]);
+  else bound = (tau_init != nullptr) ? tau_init[q] : -INFINITY;
+  __syncthreads();
+  // canonical rescoring into the upper half of the key array (n <= keep <= 256)
+  uint64_t* keys2 = sm->keys + 2048;
+  if (warp < 4) {
+    for (uint32_t first = warp * 32; first < n; first += 128) {
+      const uint32_t slot = first + lane;
+      const bool valid = slot < n;
+      uint32_t id = 0;
+      float tc = 0.f;
+      if (valid) { id = key_id(sm->keys[slot]); tc = key_score(sm->keys[slot]); }
+      const float s = canon_dot_warp<RowT>(rows, row_pitch, dp, qcanon + static_cast<int64_t>(q) * dp, id, valid, ts->tile[warp],
+                                           ts->qs[warp], lane);
+      if (valid) {
+        keys2[slot] = make_key(s, id);
+        if (max_err_bits != nullptr) atomicMax(max_err_bits, __float_as_uint(fabsf(s - tc)));
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t np = max(next_pow2(n), 2u);
+  for (uint32_t i = tid; i < np; i += blockDim.x) sm->keys[i] = (i < n) ? keys2[i] : 0ull;
+  block_bitonic_desc(sm->keys, np);
+  bool ok = true;
+  if (bound != -INFINITY) {
+    if (n < static_cast<uint32_t>(k)) ok = false;
+    else ok = key_score(sm->keys[k - 1]) > bound + eps[q];
+  }
+  if (ok) {
+    for (int i = tid; i < k; i += blockDim.x) {
+      const bool has = static_cast<uint32_t>(i) < n;
+      const uint64_t key = has ? sm->keys[i] : 0ull;
+      out_scores[static_cast<int64_t>(q) * k + i] = has ? key_score(key) : -3.402823466e+38f;
+      out_ids[static_cast<int64_t>(q) * k + i] = has ? static_cast<int64_t>(key_id(key)) + id_offset : -1;
+    }
+  } else if (tid == 0) {
     flagged[atomicAdd(n_flagged, 1)] = q;
   }
 }

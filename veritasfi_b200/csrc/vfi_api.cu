@@ -220,7 +220,7 @@ struct vfi_index {
   float* master = nullptr; // [cap_rows][dp] fp32 rows (F32 store only)
   uint32_t* xnorm_bits = nullptr;
   // options
-  int64_t opt_overfetch = 0, opt_force_path = 0, opt_profile = 0, opt_tau_hint = 0, opt_num_ctas = 0;
+  int64_t opt_overfetch = 0, opt_force_path = 0, opt_profile = 0, opt_tau_hint = 0, opt_num_ctas = 0, opt_cluster = 0;
   // workspace
   DevBuf w_qin, w_qcanon, w_qg, w_eps, w_cand, w_cand_count, w_keys, w_keys_n, w_bound, w_keys2, w_flag,
       w_out_scores, w_out_ids, w_stage, w_dbg, w_sel, w_tau;
@@ -273,7 +273,10 @@ int vfi_index_create(int d, int store_dtype, int device, vfi_index_t** out) {
   cudaEventCreate(&idx->ev1);
   cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kDenseSmemBytes);
   cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kDenseSmemBytes);
+  cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_TOPK>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
   gemv_set_smem_attr();
+  cudaFuncSetAttribute(vfi::select_rescore_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(vfi::TailSmem)));
+  cudaFuncSetAttribute(vfi::select_rescore_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(vfi::TailSmem)));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return bail(fail(VFI_ERR_CUDA, std::string("kernel attribute setup: ") + cudaGetErrorString(e)));
   *out = idx;
@@ -404,6 +407,10 @@ int vfi_index_set_option(vfi_index_t* idx, int opt, int64_t value) {
     case VFI_OPT_PROFILE: idx->opt_profile = value; break;
     case VFI_OPT_TAU_HINT: idx->opt_tau_hint = value; break;
     case VFI_OPT_NUM_CTAS: idx->opt_num_ctas = value; break;
+    case VFI_OPT_CLUSTER:
+      if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(VFI_ERR_INVALID, "cluster must be 1, 2, 4 or 8");
+      idx->opt_cluster = value;
+      break;
     default: return fail(VFI_ERR_INVALID, "unknown option");
   }
   return VFI_OK;
@@ -523,15 +530,20 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
   if (n_rows < 0) n_rows = idx->n;
   const int n_mtiles = static_cast<int>(ceil_div(nq, vfi::kBM));
   int n_ctas = idx->opt_num_ctas > 0 ? static_cast<int>(idx->opt_num_ctas) : idx->num_sms;
-  n_ctas = std::max(n_ctas, n_mtiles);
+  n_ctas = std::min(std::max(n_ctas, n_mtiles), 512);   // 2*groups key buffers per query must stay <= 1024
   const int n_tiles = static_cast<int>(ceil_div(n_rows, vfi::kBN));
   int n_groups = std::max(1, n_ctas / n_mtiles);
   n_groups = std::min(n_groups, std::max(1, n_tiles));
   const int nq_pad = n_mtiles * vfi::kBM;
   const int cap = 2 * keep + 32;
   CUtensorMap tq, td;
+  int p_cluster = 1;
   VFI_TRY(make_tmap(&tq, idx->w_qg.p, nq, idx->kp, idx->kp, vfi::kBM));
-  VFI_TRY(make_tmap(&td, idx->g, n_rows, idx->kp, idx->kp * row_stride, vfi::kBN));
+  // clusters of CTAs that work on the same corpus tile (consecutive query tiles of one group) fetch it once
+  int cluster = idx->opt_cluster > 0 ? static_cast<int>(idx->opt_cluster) : 1;
+  while (cluster > 1 && (n_mtiles % cluster) != 0) cluster >>= 1;
+  VFI_TRY(make_tmap(&td, idx->g, n_rows, idx->kp, idx->kp * row_stride, vfi::kBN / cluster));
+  p_cluster = cluster;
   vfi::DenseParams p{};
   p.nq = nq;
   p.nq_pad = nq_pad;
@@ -545,6 +557,7 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
   p.tau_init = tau;
   p.scores_out = scores_out;
   p.ld_scores = ld_scores;
+  p.cluster = p_cluster;
   if (mode == vfi::MODE_TOPK) {
     VFI_TRY(idx->w_cand.ensure(static_cast<size_t>(2 * n_groups) * nq_pad * cap * 8));
     VFI_TRY(idx->w_cand_count.ensure(static_cast<size_t>(2 * n_groups) * nq_pad * 4));
@@ -554,10 +567,20 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
   const bool prof = idx->opt_profile != 0 && profile;
   if (prof) cudaEventRecord(idx->ev0, st);
   const int grid = n_groups * n_mtiles;
-  if (mode == vfi::MODE_TOPK)
-    vfi::dense_fused_kernel<vfi::MODE_TOPK><<<grid, vfi::kDenseThreads, vfi::kDenseSmemBytes, st>>>(tq, td, p);
-  else
-    vfi::dense_fused_kernel<vfi::MODE_STORE><<<grid, vfi::kDenseThreads, vfi::kDenseSmemBytes, st>>>(tq, td, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(vfi::kDenseThreads);
+  cfg.dynamicSmemBytes = vfi::kDenseSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (mode == vfi::MODE_TOPK) VFI_CUDA(cudaLaunchKernelEx(&cfg, vfi::dense_fused_kernel<vfi::MODE_TOPK>, tq, td, p));
+  else VFI_CUDA(cudaLaunchKernelEx(&cfg, vfi::dense_fused_kernel<vfi::MODE_STORE>, tq, td, p));
   LAUNCHED();
   if (prof) cudaEventRecord(idx->ev1, st);
   VFI_CUDA(cudaGetLastError());
@@ -642,18 +665,35 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
     VFI_CUDA(cudaGetLastError());
     idx->stats.fused_launches++;
   }
-  // K1c: per-query union of the group buffers
-  VFI_TRY(idx->w_keys.ensure(static_cast<size_t>(nq) * keep * 8));
-  VFI_TRY(idx->w_keys_n.ensure(static_cast<size_t>(nq) * 4));
-  VFI_TRY(idx->w_bound.ensure(static_cast<size_t>(nq) * 4));
-  vfi::cand_reduce_kernel<<<nq, 256, sizeof(vfi::SelectSmem), st>>>(idx->w_cand.as<uint64_t>(), idx->w_cand_count.as<uint32_t>(),
-                                                                   n_groups, nq_pad, cap, keep, tau, idx->w_keys.as<uint64_t>(),
-                                                                   idx->w_keys_n.as<uint32_t>(), idx->w_bound.as<float>());
-  LAUNCHED();
-  VFI_CUDA(cudaGetLastError());
-  // K2a: canonical rescoring of the candidates
-  VFI_TRY(idx->w_keys2.ensure(static_cast<size_t>(nq) * keep * 8));
-  {
+  VFI_TRY(idx->w_flag.ensure(static_cast<size_t>(kMaxQueriesPerLaunch + 1) * 4));
+  int* d_flag = idx->w_flag.as<int>();
+  VFI_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
+  if (keep <= 256) {
+    // fused tail: union of the group buffers + k' selection + canonical rescoring + certificate in one launch
+    if (idx->store == VFI_STORE_F32)
+      vfi::select_rescore_kernel<float><<<nq, 256, sizeof(vfi::TailSmem), st>>>(
+          idx->w_cand.as<uint64_t>(), idx->w_cand_count.as<uint32_t>(), n_groups, nq_pad, cap, keep, tau, idx->master, idx->dp,
+          idx->dp, idx->w_qcanon.as<float>(), k, idx->id_offset, idx->w_eps.as<float>(), out_scores, out_ids, d_flag + 1, d_flag,
+          idx->d_max_err);
+    else
+      vfi::select_rescore_kernel<uint16_t><<<nq, 256, sizeof(vfi::TailSmem), st>>>(
+          idx->w_cand.as<uint64_t>(), idx->w_cand_count.as<uint32_t>(), n_groups, nq_pad, cap, keep, tau, idx->g, idx->kp,
+          idx->dp, idx->w_qcanon.as<float>(), k, idx->id_offset, idx->w_eps.as<float>(), out_scores, out_ids, d_flag + 1, d_flag,
+          idx->d_max_err);
+    LAUNCHED();
+    VFI_CUDA(cudaGetLastError());
+  } else {
+    // K1c: per-query union of the group buffers
+    VFI_TRY(idx->w_keys.ensure(static_cast<size_t>(nq) * keep * 8));
+    VFI_TRY(idx->w_keys_n.ensure(static_cast<size_t>(nq) * 4));
+    VFI_TRY(idx->w_bound.ensure(static_cast<size_t>(nq) * 4));
+    vfi::cand_reduce_kernel<<<nq, 256, sizeof(vfi::SelectSmem), st>>>(idx->w_cand.as<uint64_t>(), idx->w_cand_count.as<uint32_t>(),
+                                                                     n_groups, nq_pad, cap, keep, tau, idx->w_keys.as<uint64_t>(),
+                                                                     idx->w_keys_n.as<uint32_t>(), idx->w_bound.as<float>());
+    LAUNCHED();
+    VFI_CUDA(cudaGetLastError());
+    // K2a: canonical rescoring of the candidates
+    VFI_TRY(idx->w_keys2.ensure(static_cast<size_t>(nq) * keep * 8));
     dim3 grid(static_cast<unsigned>(ceil_div(keep, 128)), static_cast<unsigned>(nq));
     if (idx->store == VFI_STORE_F32)
       vfi::canon_score_kernel<float><<<grid, 128, 0, st>>>(idx->master, idx->dp, idx->dp, idx->w_qcanon.as<float>(), nullptr,
@@ -665,17 +705,14 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
                                                               idx->w_keys2.as<uint64_t>(), keep, idx->d_max_err);
     LAUNCHED();
     VFI_CUDA(cudaGetLastError());
+    // K2b: final order + certificate
+    vfi::finalize_kernel<<<nq, 256, sizeof(vfi::SelectSmem), st>>>(idx->w_keys2.as<uint64_t>(), keep, keep, nullptr,
+                                                                  idx->w_keys_n.as<uint32_t>(), k, idx->id_offset,
+                                                                  idx->w_bound.as<float>(), idx->w_eps.as<float>(), 1, out_scores,
+                                                                  out_ids, d_flag + 1, d_flag);
+    LAUNCHED();
+    VFI_CUDA(cudaGetLastError());
   }
-  // K2b: final order + certificate
-  VFI_TRY(idx->w_flag.ensure(static_cast<size_t>(kMaxQueriesPerLaunch + 1) * 4));
-  int* d_flag = idx->w_flag.as<int>();
-  VFI_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
-  vfi::finalize_kernel<<<nq, 256, sizeof(vfi::SelectSmem), st>>>(idx->w_keys2.as<uint64_t>(), keep, keep, nullptr,
-                                                                idx->w_keys_n.as<uint32_t>(), k, idx->id_offset,
-                                                                idx->w_bound.as<float>(), idx->w_eps.as<float>(), 1, out_scores,
-                                                                out_ids, d_flag + 1, d_flag);
-  LAUNCHED();
-  VFI_CUDA(cudaGetLastError());
   VFI_CUDA(cudaMemcpyAsync(idx->h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
   VFI_CUDA(cudaStreamSynchronize(st));
   if (idx->opt_profile) {
@@ -983,8 +1020,15 @@ int vfi_bm25_create(const int64_t* indptr, const int32_t* indices, const float* 
   const int64_t nnz = indptr[n_vocab];
   if (nnz < 0 || (nnz > 0 && (!indices || !data))) return fail(VFI_ERR_INVALID, "bad posting arrays");
   if (n_docs >= 0x7FFFFFF0ll) return fail(VFI_ERR_UNSUPPORTED, "a BM25 shard holds at most 2^31-16 docs");
-  for (int64_t t = 0; t < n_vocab; ++t)
+  for (int64_t t = 0; t < n_vocab; ++t) {
     if (indptr[t] > indptr[t + 1]) return fail(VFI_ERR_INVALID, "indptr must be non-decreasing");
+    // the kernel indexes its shared accumulator with these ids: every posting list must hold in-range,
+    // strictly ascending doc ids (the bm25s layout)
+    for (int64_t i = indptr[t]; i < indptr[t + 1]; ++i) {
+      if (indices[i] < 0 || indices[i] >= n_docs) return fail(VFI_ERR_INVALID, "posting doc id out of range");
+      if (i > indptr[t] && indices[i] <= indices[i - 1]) return fail(VFI_ERR_INVALID, "postings of a token must have strictly ascending doc ids");
+    }
+  }
   cudaDeviceProp prop;
   VFI_TRY(device_props(device, &prop));
   DeviceGuard guard(device);
