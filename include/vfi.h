@@ -85,6 +85,11 @@ int vfi_index_dim(const vfi_index_t* idx);
 int vfi_index_set_id_offset(vfi_index_t* idx, int64_t offset);
 /* copy row i (as fp32, the stored value) to out[d] */
 int vfi_index_reconstruct(vfi_index_t* idx, int64_t i, float* out, int mem);
+/* copy rows [first, first+n) as fp32 stored values to out[n,d] (bulk reconstruct; persisting a shard) */
+int vfi_index_read_rows(vfi_index_t* idx, int64_t first, int64_t n, float* out, int mem, void* stream);
+/* canonical scores between stored rows: out[i*n+j] = <row ids[i], row ids[j]> (fp64 sequential, rounded to fp32).
+ * With L2-normalised rows this is the cosine matrix of ensembleRetriever.py:265-281 without re-embedding. */
+int vfi_index_pairwise(vfi_index_t* idx, const int64_t* ids, int n, float* out, int mem, void* stream);
 /* exact top-k of q·xᵀ. q: fp32 [nq,d]; out_scores fp32 [nq,k]; out_ids int64 [nq,k].
  * Blocks until the results are in the caller's buffers when mem == VFI_MEM_HOST; with
  * VFI_MEM_DEVICE the call returns after the device work is enqueued and verified. */

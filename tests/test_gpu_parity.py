@@ -421,3 +421,64 @@ def test_multipath_batch_equals_stagewise_oracle(torch_cuda):
     ui, us, up = mp.multipath_batch(q, None, qs, k, fusion="union")
     vi, vs, vp, vc = ofu.union(lists, np.stack([D0, ms, Sb], axis=1))
     assert (ui.cpu().numpy() == vi[:, :k]).all() and (up.cpu().numpy() == vp[:, :k]).all()
+
+
+# ------------------------------------------------------------------------------------------------ next rows
+def test_shard_save_load_roundtrip_is_bit_exact(torch_cuda, tmp_path):
+    torch = torch_cuda
+    from veritasfi_b200.dense import DenseIndex
+    for store in ("bf16", "f32"):
+        xb, xq = _world(9000, 100, 6, 41, store == "bf16")
+        a = DenseIndex(100, store=store)
+        a.add(xb)
+        ob, _ = _oracle_inputs(xb, xq, store)
+        assert (a.read_rows(10, 500) == ob[10:510]).all()
+        a.save(str(tmp_path / store))
+        b = DenseIndex.load(str(tmp_path / store), id_offset=7)
+        assert b.ntotal == 9000 and b.store == store
+        q = torch.from_numpy(xq).cuda()
+        ia, sa = a.search_batch(q, 25)
+        ib, sb = b.search_batch(q, 25)
+        assert torch.equal(ia + 7, ib) and torch.equal(sa, sb)
+
+
+def test_pairwise_similarity_by_id_matches_oracle(torch_cuda):
+    from oracle import flat_ip
+    from veritasfi_b200.dense import DenseIndex
+    rng = np.random.default_rng(3)
+    x = flat_ip.normalize_l2(rng.standard_normal((500, 96)).astype(np.float32))
+    idx = DenseIndex(96, store="f32")
+    idx.add(x)
+    ids = [7, 7, 499, 0, 123, 250]
+    m = idx.pairwise(ids).cpu().numpy()
+    for i, a in enumerate(ids):
+        want = flat_ip.canon_scores(x[a], x, np.array(ids))
+        assert (m[i] == want).all()
+    assert np.allclose(np.diag(m), 1.0, atol=1e-6)
+
+
+def test_mirror_similarity_helpers_match_the_reference_formula(tmp_path):
+    """compute_similarity_mtx / compute_similarity (ensembleRetriever.py:235-281): normalise, then dot."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import fixture_world as fw
+    import oracle_doubles as od
+    from oracle import flat_ip
+    from veritasfi_b200 import retrievers
+    world = fw.make_world()
+    od.write_bm25_dir(world, str(tmp_path))
+    chroma, ts = fw.make_collections(world)
+    emb = fw.FakeEmbeddings(world)
+    r = retrievers.EnsembleRetriever(str(tmp_path), chroma, ts, 5, emb)
+    chunks = ["near:7:1", "near:8:2", "near:7:3", "revenue profit"]
+    m = r.compute_similarity_mtx(chunks).cpu().numpy()
+    vecs = flat_ip.normalize_l2(np.array([emb.embed_query(c) for c in chunks], dtype=np.float32))
+    ref = vecs.astype(np.float64) @ vecs.astype(np.float64).T
+    assert m.shape == (4, 4) and np.abs(m - ref).max() < 1e-6
+    for i in range(4):
+        assert (m[i] == flat_ip.canon_scores(vecs[i], vecs, np.arange(4))).all()
+    s = r.compute_similarity(chunks, [0, 1], 2).cpu().numpy()
+    assert (s == m[[0, 1], 2]).all()
+    by_row = r.similarity_mtx_by_row([3, 4, 5]).numpy()
+    xb = flat_ip.normalize_l2(world["emb"])
+    assert (by_row[0] == flat_ip.canon_scores(xb[3], xb, np.array([3, 4, 5]))).all()

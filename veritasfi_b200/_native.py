@@ -55,6 +55,8 @@ _SIGNATURES = {
     "vfi_index_dim": (C.c_int, [_P]),
     "vfi_index_set_id_offset": (C.c_int, [_P, C.c_int64]),
     "vfi_index_reconstruct": (C.c_int, [_P, C.c_int64, _P, C.c_int]),
+    "vfi_index_read_rows": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, _P]),
+    "vfi_index_pairwise": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
     "vfi_index_search": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P, C.c_int, _P]),
     "vfi_index_set_option": (C.c_int, [_P, C.c_int, C.c_int64]),
     "vfi_index_get_stats": (C.c_int, [_P, C.POINTER(SearchStats), C.c_int]),

@@ -444,6 +444,35 @@ __global__ void __launch_bounds__(256) finalize_kernel(
   }
 }
 
+// stored rows -> fp32 (bulk reconstruct) ; one thread per element
+template <typename RowT>
+__global__ void rows_to_f32_kernel(const RowT* __restrict__ rows, int64_t pitch, int64_t first, int64_t n, int d,
+                                   float* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n * d) return;
+  const int64_t r = i / d;
+  const int c = static_cast<int>(i - r * d);
+  const RowT v = rows[(first + r) * pitch + c];
+  out[i] = (sizeof(RowT) == 2) ? __uint_as_float(static_cast<uint32_t>(v) << 16) : static_cast<float>(v);
+}
+// gather rows by id as fp32 "queries" [n][dp] and as candidate keys [n] (score part unused)
+template <typename RowT>
+__global__ void gather_rows_kernel(const RowT* __restrict__ rows, int64_t pitch, const int64_t* __restrict__ ids, int n, int dp,
+                                   float* __restrict__ qout, uint64_t* __restrict__ keys, uint32_t* __restrict__ n_keys) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < static_cast<int64_t>(n) * dp) {
+    const int r = static_cast<int>(i / dp), c = static_cast<int>(i % dp);
+    const RowT v = rows[ids[r] * pitch + c];
+    qout[i] = (sizeof(RowT) == 2) ? __uint_as_float(static_cast<uint32_t>(v) << 16) : static_cast<float>(v);
+  }
+  if (i < static_cast<int64_t>(n) * n) keys[i] = make_key(0.f, static_cast<uint32_t>(ids[i % n]));
+  if (i < n) n_keys[i] = static_cast<uint32_t>(n);
+}
+__global__ void keys_to_scores_kernel(const uint64_t* __restrict__ keys, int64_t n, float* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = key_score(keys[i]);
+}
+
 // ------------------------------------------------------------------------------------------
 // K1c+K2 fused (k' <= 256): one CTA per query does the whole tail of a search — union of the group
 // buffers, k' best by tensor-core score, canonical rescoring (warps 0-3, 32 candidates each per round),

@@ -777,6 +777,92 @@ int vfi_index_search(vfi_index_t* idx, const float* q, int64_t nq, int k, float*
   return VFI_OK;
 }
 
+int vfi_index_read_rows(vfi_index_t* idx, int64_t first, int64_t n, float* out, int mem, void* stream) {
+  if (!idx || (n > 0 && !out) || first < 0 || n < 0) return fail(VFI_ERR_INVALID, "bad argument to vfi_index_read_rows");
+  if (first + n > idx->n) return fail(VFI_ERR_INVALID, "rows out of range");
+  if (n == 0) return VFI_OK;
+  std::lock_guard<std::mutex> lock(idx->mu);
+  DeviceGuard guard(idx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t chunk = std::max<int64_t>(1, (static_cast<int64_t>(256) << 20) / (static_cast<int64_t>(idx->d) * 4));
+  for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+    const int64_t rows = std::min(chunk, n - r0);
+    float* dst = out + r0 * idx->d;
+    if (mem == VFI_MEM_HOST) {
+      VFI_TRY(idx->w_stage.ensure(static_cast<size_t>(rows) * idx->d * 4));
+      dst = idx->w_stage.as<float>();
+    }
+    const unsigned blocks = static_cast<unsigned>(ceil_div(rows * idx->d, 256));
+    if (idx->store == VFI_STORE_F32)
+      vfi::rows_to_f32_kernel<float><<<blocks, 256, 0, st>>>(idx->master, idx->dp, first + r0, rows, idx->d, dst);
+    else
+      vfi::rows_to_f32_kernel<uint16_t><<<blocks, 256, 0, st>>>(idx->g, idx->kp, first + r0, rows, idx->d, dst);
+    LAUNCHED();
+    VFI_CUDA(cudaGetLastError());
+    if (mem == VFI_MEM_HOST) {
+      VFI_CUDA(cudaMemcpyAsync(out + r0 * idx->d, dst, static_cast<size_t>(rows) * idx->d * 4, cudaMemcpyDeviceToHost, st));
+      VFI_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+  VFI_CUDA(cudaStreamSynchronize(st));
+  return VFI_OK;
+}
+
+int vfi_index_pairwise(vfi_index_t* idx, const int64_t* ids, int n, float* out, int mem, void* stream) {
+  if (!idx || n < 0 || (n > 0 && (!ids || !out))) return fail(VFI_ERR_INVALID, "bad argument to vfi_index_pairwise");
+  if (n > 1024) return fail(VFI_ERR_UNSUPPORTED, "pairwise supports up to 1024 rows");
+  if (n == 0) return VFI_OK;
+  std::lock_guard<std::mutex> lock(idx->mu);
+  DeviceGuard guard(idx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<int64_t> hid(n);
+  const int64_t* dids = ids;
+  if (mem == VFI_MEM_DEVICE) VFI_CUDA(cudaMemcpyAsync(hid.data(), ids, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+  else std::memcpy(hid.data(), ids, sizeof(int64_t) * n);
+  VFI_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < n; ++i)
+    if (hid[i] < 0 || hid[i] >= idx->n) return fail(VFI_ERR_INVALID, "pairwise: row id out of range");
+  VFI_TRY(idx->w_sel.ensure(static_cast<size_t>(n) * 8));
+  if (mem == VFI_MEM_HOST) {
+    VFI_CUDA(cudaMemcpyAsync(idx->w_sel.p, hid.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
+    dids = idx->w_sel.as<int64_t>();
+  }
+  VFI_TRY(idx->w_qcanon.ensure(static_cast<size_t>(n) * idx->dp * 4));
+  VFI_TRY(idx->w_keys.ensure(static_cast<size_t>(n) * n * 8));
+  VFI_TRY(idx->w_keys2.ensure(static_cast<size_t>(n) * n * 8));
+  VFI_TRY(idx->w_keys_n.ensure(static_cast<size_t>(n) * 4));
+  const int64_t work = std::max<int64_t>(static_cast<int64_t>(n) * idx->dp, static_cast<int64_t>(n) * n);
+  const unsigned blocks = static_cast<unsigned>(ceil_div(work, 256));
+  dim3 grid(static_cast<unsigned>(ceil_div(n, 128)), static_cast<unsigned>(n));
+  if (idx->store == VFI_STORE_F32) {
+    vfi::gather_rows_kernel<float><<<blocks, 256, 0, st>>>(idx->master, idx->dp, dids, n, idx->dp, idx->w_qcanon.as<float>(),
+                                                           idx->w_keys.as<uint64_t>(), idx->w_keys_n.as<uint32_t>());
+    vfi::canon_score_kernel<float><<<grid, 128, 0, st>>>(idx->master, idx->dp, idx->dp, idx->w_qcanon.as<float>(), nullptr,
+                                                         idx->w_keys.as<uint64_t>(), idx->w_keys_n.as<uint32_t>(), n, 0,
+                                                         idx->w_keys2.as<uint64_t>(), n, nullptr);
+  } else {
+    vfi::gather_rows_kernel<uint16_t><<<blocks, 256, 0, st>>>(idx->g, idx->kp, dids, n, idx->dp, idx->w_qcanon.as<float>(),
+                                                              idx->w_keys.as<uint64_t>(), idx->w_keys_n.as<uint32_t>());
+    vfi::canon_score_kernel<uint16_t><<<grid, 128, 0, st>>>(idx->g, idx->kp, idx->dp, idx->w_qcanon.as<float>(), nullptr,
+                                                            idx->w_keys.as<uint64_t>(), idx->w_keys_n.as<uint32_t>(), n, 0,
+                                                            idx->w_keys2.as<uint64_t>(), n, nullptr);
+  }
+  LAUNCHED();
+  LAUNCHED();
+  float* dout = out;
+  if (mem == VFI_MEM_HOST) {
+    VFI_TRY(idx->w_dbg.ensure(static_cast<size_t>(n) * n * 4));
+    dout = idx->w_dbg.as<float>();
+  }
+  vfi::keys_to_scores_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(n) * n, 256)), 256, 0, st>>>(
+      idx->w_keys2.as<uint64_t>(), static_cast<int64_t>(n) * n, dout);
+  LAUNCHED();
+  VFI_CUDA(cudaGetLastError());
+  if (mem == VFI_MEM_HOST) VFI_CUDA(cudaMemcpyAsync(out, dout, static_cast<size_t>(n) * n * 4, cudaMemcpyDeviceToHost, st));
+  VFI_CUDA(cudaStreamSynchronize(st));
+  return VFI_OK;
+}
+
 int vfi_index_debug_scores(vfi_index_t* idx, const float* q, int64_t nq, float* out, int mem, void* stream) {
   if (!idx || !q || !out || nq <= 0 || nq > kMaxQueriesPerLaunch) return fail(VFI_ERR_INVALID, "bad argument to vfi_index_debug_scores");
   if (idx->n == 0) return VFI_OK;

@@ -108,6 +108,52 @@ class DenseIndex:
         N.check(N.load().vfi_index_search(self._h, C.c_void_p(q_ptr), B, int(k), C.c_void_p(scores_ptr),
                                           C.c_void_p(ids_ptr), N.MEM_HOST, None))
 
+    # -- persist / reload a shard -------------------------------------------------
+    def read_rows(self, first: int = 0, n: int | None = None) -> np.ndarray:
+        """Stored rows [first, first+n) as float32 (bf16 rows are exactly representable)."""
+        n = self.ntotal - first if n is None else n
+        out = np.empty((n, self.d), dtype=np.float32)
+        if n:
+            N.check(N.load().vfi_index_read_rows(self._h, int(first), int(n), out.ctypes.data_as(C.c_void_p), N.MEM_HOST, None))
+        return out
+
+    def save(self, path: str, chunk: int = 1 << 18) -> None:
+        """<path>.json (d, store, ntotal, id_offset) + <path>.rows.npy (float32 rows; reloading is bit-exact)."""
+        import json
+        n = self.ntotal
+        mm = np.lib.format.open_memmap(path + ".rows.npy", mode="w+", dtype=np.float32, shape=(n, self.d))
+        for r0 in range(0, n, chunk):
+            r1 = min(n, r0 + chunk)
+            mm[r0:r1] = self.read_rows(r0, r1 - r0)
+        mm.flush()
+        del mm
+        with open(path + ".json", "w") as f:
+            json.dump({"d": self.d, "store": self.store, "ntotal": n, "format": "vfi-dense-shard-1"}, f)
+
+    @classmethod
+    def load(cls, path: str, device: int | torch.device = 0, id_offset: int = 0, chunk: int = 1 << 18) -> "DenseIndex":
+        import json
+        with open(path + ".json") as f:
+            meta = json.load(f)
+        rows = np.load(path + ".rows.npy", mmap_mode="r")
+        self = cls(meta["d"], store=meta["store"], device=device, id_offset=id_offset)
+        self.reserve(meta["ntotal"])
+        for r0 in range(0, meta["ntotal"], chunk):
+            self.add(np.ascontiguousarray(rows[r0:r0 + chunk]))
+        return self
+
+    # -- SURVEY.md §8f N3: similarity between stored rows, by id -------------------------------------
+    def pairwise(self, ids) -> torch.Tensor:
+        """out[i, j] = canonical <row ids[i], row ids[j]> on the GPU; with L2-normalised rows this is the cosine
+        matrix of ensembleRetriever.py:265-281 without re-embedding any chunk text."""
+        ids_t = torch.as_tensor(ids, dtype=torch.int64, device=self.device).contiguous()
+        n = ids_t.numel()
+        out = torch.empty((n, n), dtype=torch.float32, device=self.device)
+        if n:
+            N.check(N.load().vfi_index_pairwise(self._h, C.c_void_p(ids_t.data_ptr()), n, C.c_void_p(out.data_ptr()),
+                                                N.MEM_DEVICE, _stream_ptr(self.device)))
+        return out
+
     def debug_scores(self, q: torch.Tensor) -> torch.Tensor:
         """Raw tensor-core scores [B, ntotal] (test hook for the tcgen05 path)."""
         q = q.contiguous()

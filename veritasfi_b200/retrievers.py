@@ -163,6 +163,42 @@ class EnsembleRetriever:
             if not grew:
                 break
 
+    # -- near-duplicate helpers used by the reranker (ensembleRetriever.py:235-281) ----------------
+    def _embed_normalised_index(self, chunks: List[str]):
+        from .dense import DenseIndex
+        vecs = np.ascontiguousarray(np.array([self.embeddings.embed_query(c) for c in chunks]).astype("float32"))
+        device = self.faiss_retriever.index.device
+        faiss_compat.normalize_L2(vecs, device=device)
+        tmp = DenseIndex(vecs.shape[1], store="f32", device=device)
+        tmp.add(vecs)
+        return tmp
+
+    def compute_similarity(self, chunks: List[str], selected_indices: List[int], candidate_index: int):
+        """Cosine similarity between chunk `candidate_index` and the chunks `selected_indices` (a cuda tensor)."""
+        tmp = self._embed_normalised_index(chunks)
+        ids = list(selected_indices) + [candidate_index]
+        m = tmp.pairwise(ids)
+        return m[:-1, -1].clone()
+
+    def compute_similarity_mtx(self, chunks: List[str]):
+        """Pairwise cosine similarity of the chunks (a cuda tensor [n, n])."""
+        tmp = self._embed_normalised_index(chunks)
+        return tmp.pairwise(range(len(chunks)))
+
+    def similarity_mtx_by_row(self, rows: List[int]):
+        """The same matrix for chunks already in the index, addressed by row id: no re-embedding."""
+        from .dense import DenseIndex  # noqa: F401
+        import ctypes as C
+        import torch
+        from . import _native as N
+        idx = self.faiss_retriever.index
+        ids = np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.empty((len(ids), len(ids)), dtype=np.float32)
+        if len(ids):
+            N.check(N.load().vfi_index_pairwise(idx._h, ids.ctypes.data_as(C.c_void_p), len(ids), out.ctypes.data_as(C.c_void_p),
+                                                N.MEM_HOST, None))
+        return torch.from_numpy(out)
+
     # -- the call the rest of the pipeline makes -------------------------------------------------
     @profiler.profile_function(name="retrieve")
     def invoke(self, input: str, hyde_chunks: list[str]) -> List[Dict]:
