@@ -36,6 +36,7 @@ WORKLOADS = {
     "c3": dict(n=10_000_000, d=1024, b=1024, k=100, desc="10Mx1024 bf16 corpus, 1024-query batch, top-100 (BASELINE configs[2])"),
     "c2": dict(n=1_000_000, d=1024, b=256, k=100, desc="1Mx1024 bf16 corpus, 256-query batch, top-100 (BASELINE configs[1])"),
     "c5": dict(n=50_000_000, d=768, b=1, k=10, desc="50Mx768 bf16 corpus, single query, top-10 (BASELINE configs[4])"),
+    "c3s8": dict(n=1_250_000, d=1024, b=1024, k=100, desc="one 1/8 row shard of C3 (1.25Mx1024 bf16), 1024-query batch, top-100"),
     "small": dict(n=200_000, d=1024, b=256, k=100, desc="200kx1024 smoke-size workload"),
 }
 SEED = 1234 + 2

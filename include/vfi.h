@@ -103,7 +103,9 @@ enum {
   VFI_OPT_PROFILE = 3,       /* 1: bracket the dominant kernel with CUDA events */
   VFI_OPT_TAU_HINT = 4,      /* 1: estimate a per-query admission threshold from a row sample (2: debug, admit nothing) */
   VFI_OPT_NUM_CTAS = 5,      /* 0 = one CTA per SM */
-  VFI_OPT_CLUSTER = 6        /* CTAs per thread-block cluster sharing corpus tiles by TMA multicast: 0/1 off, 2, 4, 8 */
+  VFI_OPT_CLUSTER = 6,       /* single-CTA kernel only: CTAs per cluster sharing corpus tiles by TMA multicast: 0/1 off, 2, 4, 8 */
+  VFI_OPT_CTA_PAIR = 7       /* tcgen05 cta_group::2 kernel (two SMs share every corpus tile): 0 auto (on when the batch has an
+                                even number of 128-query tiles), 1 off, 2 on */
 };
 int vfi_index_set_option(vfi_index_t* idx, int opt, int64_t value);
 
@@ -139,6 +141,28 @@ int vfi_cosine_topk(const float* e, int64_t n_e, const float* c, int64_t n_c, in
 int vfi_merge_topk(const float* scores, const int64_t* ids, int g, int64_t nq, int k_in,
                    int k_out, float* out_scores, int64_t* out_ids, int mem, int device,
                    void* stream);
+
+/* ---- multi-GPU exchange + merge over peer memory (one process per GPU) ----------------------- */
+/* The fused form of "all-gather the per-shard results, then vfi_merge_topk": every rank owns a receive
+ * window in its HBM that its peers map through CUDA IPC; ONE kernel per rank stores the rank's [nq,k]
+ * results straight into every peer's window over NVLink, publishes per-query flags, waits for the
+ * peers' flags and selects the global top-k_out.  No reference counterpart (workers are replicas,
+ * experiments/retriever/step3_mul.py:405-446).  Usage, identically on every rank:
+ *   vfi_exchange_create -> vfi_exchange_handle -> (host all-gathers the 64-byte handles, any transport)
+ *   -> vfi_exchange_connect -> (host barrier) -> vfi_exchange_merge ... -> (host barrier) -> destroy.
+ * vfi_exchange_merge is a collective: all ranks call it the same number of times with the same nq, k.
+ * ids are global and must be < 2^32 - 1 (as for vfi_merge_topk); -1 = padding.  All buffers are device
+ * memory.  A peer that does not arrive within the timeout (default 30 s) traps the kernel (sticky CUDA
+ * error) instead of hanging the GPU.  world <= 16.  Never run two ranks on one GPU. */
+typedef struct vfi_exchange vfi_exchange_t;
+#define VFI_IPC_HANDLE_BYTES 64
+int vfi_exchange_create(int device, int rank, int world, int64_t max_nq, int max_k, vfi_exchange_t** out);
+int vfi_exchange_handle(vfi_exchange_t* ex, void* out_handle /* VFI_IPC_HANDLE_BYTES */);
+int vfi_exchange_connect(vfi_exchange_t* ex, const void* handles /* world x VFI_IPC_HANDLE_BYTES, rank order */);
+int vfi_exchange_set_timeout_ms(vfi_exchange_t* ex, int64_t ms);
+int vfi_exchange_merge(vfi_exchange_t* ex, const float* scores, const int64_t* ids, int64_t nq, int k, int k_out,
+                       float* out_scores, int64_t* out_ids, void* stream);
+int vfi_exchange_destroy(vfi_exchange_t* ex);
 
 /* ---- BM25 over token-major postings (bm25s CSC arrays) ----------------------------------- */
 /* indptr int64 [n_vocab+1], indices int32 [nnz] (doc ids ascending per token), data fp32 [nnz]

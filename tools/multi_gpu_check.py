@@ -1,6 +1,6 @@
 """Multi-GPU parity check, launched one process per GPU:
     python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P tools/multi_gpu_check.py
-Every rank holds a row shard of one seeded corpus; the NCCL all-gather + merge kernel result must equal the
+Every rank holds a row shard of one seeded corpus; the fused peer-memory exchange and the NCCL all-gather + merge kernel results must equal the
 unsharded CPU oracle bit for bit."""
 import os
 import sys
@@ -34,11 +34,16 @@ def main():
         idx.add(xb[lo:hi])
         idx.set_option(N.OPT_FORCE_PATH, path)
         idx.set_option(N.OPT_TAU_HINT, 1)
-        searcher = make_sharded_dense(idx)
-        ids, scores = searcher.search(torch.from_numpy(xq).to(dev), k)
-        torch.cuda.synchronize()
         D0, I0 = flat_ip.search(xq, xb, k)
-        good = bool((ids.cpu().numpy() == I0).all() and (scores.cpu().numpy() == D0).all())
+        good = True
+        for mode in ("peer", "nccl"):          # fused peer-memory kernel and the all-gather route: same bits
+            searcher = make_sharded_dense(idx, exchange=mode)
+            for rep in range(3):               # repeated epochs exercise both window parities
+                ids, scores = searcher.search(torch.from_numpy(xq).to(dev), k)
+                torch.cuda.synchronize()
+                good &= bool((ids.cpu().numpy() == I0).all() and (scores.cpu().numpy() == D0).all())
+            if searcher.exchange is not None:
+                searcher.exchange.close()
         flag = torch.tensor([1 if good else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:

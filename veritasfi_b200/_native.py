@@ -11,9 +11,10 @@ from .build import LIB_PATH
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_INTERNAL = range(7)
 MEM_HOST, MEM_DEVICE = 0, 1
 STORE_BF16, STORE_F32 = 0, 1
-OPT_OVERFETCH, OPT_FORCE_PATH, OPT_PROFILE, OPT_TAU_HINT, OPT_NUM_CTAS, OPT_CLUSTER = 1, 2, 3, 4, 5, 6
+OPT_OVERFETCH, OPT_FORCE_PATH, OPT_PROFILE, OPT_TAU_HINT, OPT_NUM_CTAS, OPT_CLUSTER, OPT_CTA_PAIR = 1, 2, 3, 4, 5, 6, 7
 PATH_AUTO, PATH_EXHAUSTIVE, PATH_FUSED, PATH_GEMV = 0, 1, 2, 3
 MAX_K = 2048
+IPC_HANDLE_BYTES = 64
 
 
 class VfiError(RuntimeError):
@@ -64,6 +65,12 @@ _SIGNATURES = {
     "vfi_normalize_l2": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),
     "vfi_cosine_topk": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
     "vfi_merge_topk": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
+    "vfi_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(_P)]),
+    "vfi_exchange_handle": (C.c_int, [_P, _P]),
+    "vfi_exchange_connect": (C.c_int, [_P, _P]),
+    "vfi_exchange_set_timeout_ms": (C.c_int, [_P, C.c_int64]),
+    "vfi_exchange_merge": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P]),
+    "vfi_exchange_destroy": (C.c_int, [_P]),
     "vfi_bm25_create": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(_P)]),
     "vfi_bm25_destroy": (C.c_int, [_P]),
     "vfi_bm25_ndocs": (C.c_int64, [_P]),

@@ -59,6 +59,107 @@ struct DenseParams {
   int cluster;            // CTAs per cluster (1, 2, 4 or 8; divides n_mtiles): they share each corpus tile by TMA multicast
 };
 
+// ===================== epilogue: TMEM -> registers -> threshold filter =====================
+// Run by warps 4..11 of a CTA.  Two warp sets: set 0 (warps 4-7) drains accumulator stage 0 = the even tiles of
+// this CTA, set 1 (warps 8-11) stage 1 = the odd tiles, so two tiles are filtered concurrently.  Each set keeps
+// its own threshold and key buffer per query.  arrive_tempty(acc) hands the accumulator stage back to the MMA
+// issuer (a local arrive for the single-CTA kernel, a remote one on the leader for the CTA-pair kernel).
+template <int MODE, class ArriveFn>
+__device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t tmem_base, uint32_t warp, uint32_t lane,
+                                               int m_tile, int group, uint64_t* tfull_bar, uint32_t* hist,
+                                               ArriveFn arrive_tempty) {
+  const uint32_t set = (warp - 4) >> 2;
+  const uint32_t wq = (warp - 4) & 3;            // TMEM lane quadrant of this warp (= warp % 4)
+  const int qi = m_tile * kBM + wq * 32 + lane;  // the query this thread owns
+  const bool valid_q = qi < p.nq;
+  uint32_t* my_hist = hist + (warp - 4) * 256;
+
+  uint64_t* buf = nullptr;
+  uint32_t count = 0;
+  uint64_t tau_key = kKeyNone;
+  float tau_f = -INFINITY;
+  const size_t slot = (static_cast<size_t>(group) * 2 + set) * p.nq_pad + qi;
+  if (MODE == MODE_TOPK) {
+    buf = p.cand + slot * p.cap;
+    if (valid_q && p.tau_init != nullptr) {
+      tau_f = p.tau_init[qi];
+      tau_key = make_key(tau_f, 0u);   // admits score > hint only
+    }
+  }
+  const uint32_t acc = set;
+  uint32_t acc_phase = 0;
+  int local_tile = 0;
+  for (int t = group; t < p.n_tiles; t += p.n_groups, ++local_tile) {
+    if ((local_tile & 1) != static_cast<int>(set)) continue;
+    ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+    acc_phase ^= 1;
+    ptx::tc_fence_after();
+    const uint32_t row0 = static_cast<uint32_t>(t) * kBN;
+    const uint32_t taddr = tmem_base + ((wq * 32u) << 16) + acc * kBN;
+#pragma unroll 1
+    for (int c = 0; c < kBN / 32; ++c) {
+      float v[32];
+      ptx::tmem_ld_32x32(taddr + c * 32, v);
+      ptx::tmem_ld_wait();
+      if (MODE == MODE_STORE) {
+        if (valid_q) {
+          float4* dst = reinterpret_cast<float4*>(p.scores_out + static_cast<size_t>(qi) * p.ld_scores +
+                                                  row0 + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      } else {
+        // group maxima (4 columns each) feed both the chunk test and the per-group tests
+        float m4[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          m4[g] = fmaxf(fmaxf(v[4 * g], v[4 * g + 1]), fmaxf(v[4 * g + 2], v[4 * g + 3]));
+        const float mx = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])),
+                               fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
+        if (valid_q && mx >= tau_f) {
+          const uint32_t id0 = row0 + c * 32;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (m4[g] >= tau_f) {
+#pragma unroll
+              for (int j = 4 * g; j < 4 * g + 4; ++j) {
+                if (v[j] >= tau_f && id0 + j < static_cast<uint32_t>(p.n_rows)) {
+                  const uint64_t key = make_key(v[j], id0 + j);
+                  if (key > tau_key) buf[count++] = key;
+                }
+              }
+            }
+          }
+        }
+        // a buffer that cannot take another 32 keys is compacted now (warp-cooperative)
+        uint32_t need = __ballot_sync(0xFFFFFFFFu, count + 32 > static_cast<uint32_t>(p.cap));
+        while (need) {
+          const uint32_t src = __ffs(need) - 1;
+          need &= need - 1;
+          uint64_t* sbuf = reinterpret_cast<uint64_t*>(
+              __shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(buf), src));
+          const uint32_t sn = __shfl_sync(0xFFFFFFFFu, count, src);
+          __syncwarp();
+          const uint64_t kth = warp_select_compact(sbuf, sn, p.keep, my_hist, lane);
+          if (lane == src) {
+            count = p.keep;
+            tau_key = kth;
+            tau_f = key_score(kth);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) arrive_tempty(acc);
+  }
+  if (MODE == MODE_TOPK) {
+    p.cand_count[slot] = valid_q ? count : 0u;
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kDenseThreads, 1)
 dense_fused_kernel(const __grid_constant__ CUtensorMap tmap_q,
@@ -160,100 +261,8 @@ dense_fused_kernel(const __grid_constant__ CUtensorMap tmap_q,
       if (acc == 0) acc_phase ^= 1;
     }
   } else if (active && warp >= 4) {
-    // ===================== epilogue: TMEM -> registers -> threshold filter =====================
-    // Two warp sets: set 0 (warps 4-7) drains accumulator stage 0 = the even tiles of this CTA, set 1
-    // (warps 8-11) stage 1 = the odd tiles, so two tiles are filtered concurrently.  Each set keeps its
-    // own threshold and key buffer per query.
-    const uint32_t set = (warp - 4) >> 2;
-    const uint32_t wq = (warp - 4) & 3;            // TMEM lane quadrant of this warp (= warp % 4)
-    const int qi = m_tile * kBM + wq * 32 + lane;  // the query this thread owns
-    const bool valid_q = qi < p.nq;
-    uint32_t* my_hist = hist + (warp - 4) * 256;
-
-    uint64_t* buf = nullptr;
-    uint32_t count = 0;
-    uint64_t tau_key = kKeyNone;
-    float tau_f = -INFINITY;
-    const size_t slot = (static_cast<size_t>(group) * 2 + set) * p.nq_pad + qi;
-    if (MODE == MODE_TOPK) {
-      buf = p.cand + slot * p.cap;
-      if (valid_q && p.tau_init != nullptr) {
-        tau_f = p.tau_init[qi];
-        tau_key = make_key(tau_f, 0u);   // admits score > hint only
-      }
-    }
-    const uint32_t acc = set;
-    uint32_t acc_phase = 0;
-    int local_tile = 0;
-    for (int t = group; t < p.n_tiles; t += p.n_groups, ++local_tile) {
-      if ((local_tile & 1) != static_cast<int>(set)) continue;
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
-      acc_phase ^= 1;
-      ptx::tc_fence_after();
-      const uint32_t row0 = static_cast<uint32_t>(t) * kBN;
-      const uint32_t taddr = tmem_base + ((wq * 32u) << 16) + acc * kBN;
-#pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
-        float v[32];
-        ptx::tmem_ld_32x32(taddr + c * 32, v);
-        ptx::tmem_ld_wait();
-        if (MODE == MODE_STORE) {
-          if (valid_q) {
-            float4* dst = reinterpret_cast<float4*>(p.scores_out + static_cast<size_t>(qi) * p.ld_scores +
-                                                    row0 + c * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-        } else {
-          // group maxima (4 columns each) feed both the chunk test and the per-group tests
-          float m4[8];
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            m4[g] = fmaxf(fmaxf(v[4 * g], v[4 * g + 1]), fmaxf(v[4 * g + 2], v[4 * g + 3]));
-          const float mx = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])),
-                                 fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
-          if (valid_q && mx >= tau_f) {
-            const uint32_t id0 = row0 + c * 32;
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              if (m4[g] >= tau_f) {
-#pragma unroll
-                for (int j = 4 * g; j < 4 * g + 4; ++j) {
-                  if (v[j] >= tau_f && id0 + j < static_cast<uint32_t>(p.n_rows)) {
-                    const uint64_t key = make_key(v[j], id0 + j);
-                    if (key > tau_key) buf[count++] = key;
-                  }
-                }
-              }
-            }
-          }
-          // a buffer that cannot take another 32 keys is compacted now (warp-cooperative)
-          uint32_t need = __ballot_sync(0xFFFFFFFFu, count + 32 > static_cast<uint32_t>(p.cap));
-          while (need) {
-            const uint32_t src = __ffs(need) - 1;
-            need &= need - 1;
-            uint64_t* sbuf = reinterpret_cast<uint64_t*>(
-                __shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(buf), src));
-            const uint32_t sn = __shfl_sync(0xFFFFFFFFu, count, src);
-            __syncwarp();
-            const uint64_t kth = warp_select_compact(sbuf, sn, p.keep, my_hist, lane);
-            if (lane == src) {
-              count = p.keep;
-              tau_key = kth;
-              tau_f = key_score(kth);
-            }
-            __syncwarp();
-          }
-        }
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-    }
-    if (MODE == MODE_TOPK) {
-      p.cand_count[slot] = valid_q ? count : 0u;
-    }
+    dense_epilogue<MODE>(p, tmem_base, warp, lane, m_tile, group, tfull_bar, hist,
+                         [&](uint32_t a) { ptx::mbar_arrive(&tempty_bar[a]); });
   }
 
   // teardown (no CTA may leave while a peer can still multicast into it or signal its barriers)
@@ -263,6 +272,134 @@ dense_fused_kernel(const __grid_constant__ CUtensorMap tmap_q,
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ==================================================================================================
+// K1 CTA-pair variant (tcgen05 cta_group::2).  Two CTAs on the two SMs of a TPC own two adjacent query tiles
+// (M = 256 over the pair) and work on the SAME corpus tile: each CTA stages only its own 128-query A block and
+// ONE HALF (128 rows) of the 256-row corpus tile; the leader's single MMA thread issues
+// tcgen05.mma.cta_group::2 and the tensor cores of both SMs read the other half of B through the pair link.
+// Against the single-CTA kernel this cuts the L2->SM fill per FLOP by a third (512 KB instead of 768 KB per
+// CTA and corpus tile) and the shared-memory operand reads per MMA from 12 KB to 8 KB.  Measured reason: under
+// the 1 kW power cap the single-CTA kernel drops the SM clock to ~960-1140 MHz where cuBLAS holds ~1335 MHz on the
+// same box (profiles/): the fill traffic, not the MMA, was the power hog.
+// Barriers: full[s] lives in the leader and counts the TMA bytes of BOTH CTAs; empty[s] and tfull[a] exist in both
+// CTAs and are signalled by one multicast tcgen05.commit; tempty[a] lives in the leader and collects the 8 epilogue
+// warps of the pair (the peer's arrive remotely).
+// ==================================================================================================
+constexpr int kPairStages = 6;
+constexpr int kPairBBytes = (kBN / 2) * kBK * 2;   // 16 KB: this CTA's half of the corpus tile
+constexpr int kPairSmemBytes =
+    1024 /*align slack*/ + kPairStages * (kABytes + kPairBBytes) + 256 /*barriers*/ + 8 * 256 * 4 /*hist*/;
+
+template <int MODE>
+__global__ void __launch_bounds__(kDenseThreads, 1)
+dense_fused_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                        const __grid_constant__ CUtensorMap tmap_d /* box = 128 rows */, const DenseParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kPairStages * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kPairStages * kPairBBytes);
+  uint64_t* full_bar = bars;                          // [kPairStages]  TMA (both CTAs) -> MMA     (used in the leader)
+  uint64_t* empty_bar = bars + kPairStages;           // [kPairStages]  MMA -> TMA                 (both CTAs)
+  uint64_t* tfull_bar = bars + 2 * kPairStages;       // [2]            MMA -> epilogue            (both CTAs)
+  uint64_t* tempty_bar = bars + 2 * kPairStages + 2;  // [2]            epilogues of the pair -> MMA (leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairStages + 4);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 256);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t crank = ptx::cluster_ctarank();      // 0 = leader
+  const bool leader = crank == 0;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_q);
+    ptx::prefetch_tmap(&tmap_d);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kPairStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull_bar[i], 1);
+      ptx::mbar_init(&tempty_bar[i], 8);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {                                    // the same warp of BOTH CTAs: a pair-wide allocation
+    ptx::tmem_alloc_pair(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();                            // the peer's barriers and TMEM exist before anything is signalled
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int pair = static_cast<int>(blockIdx.x) >> 1;
+  const int n_mpairs = p.n_mtiles >> 1;
+  const int m_tile = (pair % n_mpairs) * 2 + static_cast<int>(crank);
+  const int group = pair / n_mpairs;
+  const bool active = group < p.n_groups;
+  const int nkb = p.n_kblocks;
+
+  if (active && warp == 0 && lane == 0) {
+    // ===================== TMA producer (one per CTA) =====================
+    uint32_t stage = 0, phase = 0;
+    const uint64_t d_hint = (p.n_mtiles > 2) ? ptx::kEvictNormal : ptx::kEvictFirst;
+    for (int t = group; t < p.n_tiles; t += p.n_groups) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        const uint32_t full_leader = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0u);
+        if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * (kABytes + kPairBBytes));
+        ptx::tma_load_2d_pair(sA + stage * kABytes, &tmap_q, full_leader, kb * kBK, m_tile * kBM, ptx::kEvictLast);
+        ptx::tma_load_2d_pair(sB + stage * kPairBBytes, &tmap_d, full_leader, kb * kBK,
+                              t * kBN + static_cast<int>(crank) * (kBN / 2), d_hint);
+        if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (active && leader && warp == 1 && lane == 0) {
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * kBM, kBN);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int t = group; t < p.n_tiles; t += p.n_groups) {
+      ptx::mbar_wait_cluster_acquire(&tempty_bar[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kBN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t a_addr = ptx::smem_u32(sA + stage * kABytes);
+        const uint32_t b_addr = ptx::smem_u32(sB + stage * kPairBBytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          ptx::umma_bf16_ss_pair(d_tmem, ptx::umma_desc_k128(a_addr + k * 32), ptx::umma_desc_k128(b_addr + k * 32),
+                                 idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        ptx::tc_commit_pair_mcast(&empty_bar[stage], 3);            // frees the stage in both CTAs when the MMAs retire
+        if (kb == nkb - 1) ptx::tc_commit_pair_mcast(&tfull_bar[acc], 3);   // accumulator complete, both epilogues
+        if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (active && warp >= 4) {
+    const uint32_t tempty_leader = ptx::mapa_u32(ptx::smem_u32(&tempty_bar[0]), 0u);
+    dense_epilogue<MODE>(p, tmem_base, warp, lane, m_tile, group, tfull_bar, hist,
+                         [&](uint32_t a) { ptx::mbar_arrive_cluster(tempty_leader + a * 8u); });
+  }
+
+  // teardown: nobody leaves while the peer can still signal its barriers or read its shared memory
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
   }
 }
 

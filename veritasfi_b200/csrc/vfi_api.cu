@@ -19,6 +19,7 @@
 #include "dense_fused.cuh"
 #include "dense_support.cuh"
 #include "sparse_fuse.cuh"
+#include "peer_exchange.cuh"
 
 namespace {
 
@@ -220,7 +221,7 @@ struct vfi_index {
   float* master = nullptr; // [cap_rows][dp] fp32 rows (F32 store only)
   uint32_t* xnorm_bits = nullptr;
   // options
-  int64_t opt_overfetch = 0, opt_force_path = 0, opt_profile = 0, opt_tau_hint = 0, opt_num_ctas = 0, opt_cluster = 0;
+  int64_t opt_overfetch = 0, opt_force_path = 0, opt_profile = 0, opt_tau_hint = 0, opt_num_ctas = 0, opt_cluster = 0, opt_cta_pair = 0;
   // workspace
   DevBuf w_qin, w_qcanon, w_qg, w_eps, w_cand, w_cand_count, w_keys, w_keys_n, w_bound, w_keys2, w_flag,
       w_out_scores, w_out_ids, w_stage, w_dbg, w_sel, w_tau;
@@ -274,6 +275,8 @@ int vfi_index_create(int d, int store_dtype, int device, vfi_index_t** out) {
   cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kDenseSmemBytes);
   cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kDenseSmemBytes);
   cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_TOPK>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+  cudaFuncSetAttribute(vfi::dense_fused_pair_kernel<vfi::MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kPairSmemBytes);
+  cudaFuncSetAttribute(vfi::dense_fused_pair_kernel<vfi::MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kPairSmemBytes);
   gemv_set_smem_attr();
   cudaFuncSetAttribute(vfi::select_rescore_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(vfi::TailSmem)));
   cudaFuncSetAttribute(vfi::select_rescore_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(vfi::TailSmem)));
@@ -407,6 +410,10 @@ int vfi_index_set_option(vfi_index_t* idx, int opt, int64_t value) {
     case VFI_OPT_PROFILE: idx->opt_profile = value; break;
     case VFI_OPT_TAU_HINT: idx->opt_tau_hint = value; break;
     case VFI_OPT_NUM_CTAS: idx->opt_num_ctas = value; break;
+    case VFI_OPT_CTA_PAIR:
+      if (value < 0 || value > 2) return fail(VFI_ERR_INVALID, "VFI_OPT_CTA_PAIR: 0 auto, 1 off, 2 on");
+      idx->opt_cta_pair = value;
+      break;
     case VFI_OPT_CLUSTER:
       if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(VFI_ERR_INVALID, "cluster must be 1, 2, 4 or 8");
       idx->opt_cluster = value;
@@ -529,6 +536,9 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
                  bool profile = true) {
   if (n_rows < 0) n_rows = idx->n;
   const int n_mtiles = static_cast<int>(ceil_div(nq, vfi::kBM));
+  // CTA pairs (tcgen05 cta_group::2) need an even number of query tiles; they are the default where possible
+  // because they move a third less data per FLOP into the SMs (the single-CTA kernel is power-capped first).
+  const bool pair = (n_mtiles % 2 == 0) && idx->opt_cta_pair != 1 && idx->opt_cluster <= 1;
   int n_ctas = idx->opt_num_ctas > 0 ? static_cast<int>(idx->opt_num_ctas) : idx->num_sms;
   n_ctas = std::min(std::max(n_ctas, n_mtiles), 512);   // 2*groups key buffers per query must stay <= 1024
   const int n_tiles = static_cast<int>(ceil_div(n_rows, vfi::kBN));
@@ -537,13 +547,12 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
   const int nq_pad = n_mtiles * vfi::kBM;
   const int cap = 2 * keep + 32;
   CUtensorMap tq, td;
-  int p_cluster = 1;
   VFI_TRY(make_tmap(&tq, idx->w_qg.p, nq, idx->kp, idx->kp, vfi::kBM));
   // clusters of CTAs that work on the same corpus tile (consecutive query tiles of one group) fetch it once
   int cluster = idx->opt_cluster > 0 ? static_cast<int>(idx->opt_cluster) : 1;
   while (cluster > 1 && (n_mtiles % cluster) != 0) cluster >>= 1;
+  if (pair) cluster = 2;
   VFI_TRY(make_tmap(&td, idx->g, n_rows, idx->kp, idx->kp * row_stride, vfi::kBN / cluster));
-  p_cluster = cluster;
   vfi::DenseParams p{};
   p.nq = nq;
   p.nq_pad = nq_pad;
@@ -557,7 +566,7 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
   p.tau_init = tau;
   p.scores_out = scores_out;
   p.ld_scores = ld_scores;
-  p.cluster = p_cluster;
+  p.cluster = cluster;
   if (mode == vfi::MODE_TOPK) {
     VFI_TRY(idx->w_cand.ensure(static_cast<size_t>(2 * n_groups) * nq_pad * cap * 8));
     VFI_TRY(idx->w_cand_count.ensure(static_cast<size_t>(2 * n_groups) * nq_pad * 4));
@@ -570,7 +579,7 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(vfi::kDenseThreads);
-  cfg.dynamicSmemBytes = vfi::kDenseSmemBytes;
+  cfg.dynamicSmemBytes = pair ? vfi::kPairSmemBytes : vfi::kDenseSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -579,8 +588,13 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (mode == vfi::MODE_TOPK) VFI_CUDA(cudaLaunchKernelEx(&cfg, vfi::dense_fused_kernel<vfi::MODE_TOPK>, tq, td, p));
-  else VFI_CUDA(cudaLaunchKernelEx(&cfg, vfi::dense_fused_kernel<vfi::MODE_STORE>, tq, td, p));
+  if (pair) {
+    if (mode == vfi::MODE_TOPK) VFI_CUDA(cudaLaunchKernelEx(&cfg, vfi::dense_fused_pair_kernel<vfi::MODE_TOPK>, tq, td, p));
+    else VFI_CUDA(cudaLaunchKernelEx(&cfg, vfi::dense_fused_pair_kernel<vfi::MODE_STORE>, tq, td, p));
+  } else {
+    if (mode == vfi::MODE_TOPK) VFI_CUDA(cudaLaunchKernelEx(&cfg, vfi::dense_fused_kernel<vfi::MODE_TOPK>, tq, td, p));
+    else VFI_CUDA(cudaLaunchKernelEx(&cfg, vfi::dense_fused_kernel<vfi::MODE_STORE>, tq, td, p));
+  }
   LAUNCHED();
   if (prof) cudaEventRecord(idx->ev1, st);
   VFI_CUDA(cudaGetLastError());
@@ -1073,6 +1087,156 @@ int vfi_cosine_topk(const float* e, int64_t n_e, const float* c, int64_t n_c, in
   if (rc != VFI_OK) return rc;
   for (int64_t i = 0; i < n_e * k; ++i)
     if (out_ids[i] >= 0) out_ids[i] = n_c - 1 - out_ids[i];
+  return VFI_OK;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// K3p: peer-memory exchange + merge (multi-GPU, one process per GPU)
+// =============================================================================================
+struct vfi_exchange {
+  int device = 0, rank = 0, world = 1, max_k = 0, num_sms = 148, max_resident = 148;
+  int64_t max_nq = 0;
+  size_t win_bytes = 0, total_bytes = 0;
+  uint8_t* local = nullptr;                 // own window + flags (cudaMalloc, exported by CUDA IPC)
+  uint8_t* peer[vfi::kMaxPeers] = {};       // every rank's window as mapped here (peer[rank] == local)
+  bool connected = false;
+  uint32_t epoch = 0;
+  uint64_t timeout_ms = 30000;
+  std::mutex mu;
+};
+
+extern "C" {
+
+int vfi_exchange_create(int device, int rank, int world, int64_t max_nq, int max_k, vfi_exchange_t** out) {
+  if (!out || world < 1 || world > vfi::kMaxPeers || rank < 0 || rank >= world || max_nq <= 0 || max_k <= 0 || max_k > VFI_MAX_K)
+    return fail(VFI_ERR_INVALID, "bad argument to vfi_exchange_create (world <= 16, 0 < max_k <= VFI_MAX_K)");
+  *out = nullptr;
+  cudaDeviceProp prop;
+  VFI_TRY(device_props(device, &prop));
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(VFI_ERR_CUDA, "cudaSetDevice failed");
+  auto* ex = new vfi_exchange();
+  ex->device = device;
+  ex->rank = rank;
+  ex->world = world;
+  ex->max_nq = max_nq;
+  ex->max_k = max_k;
+  ex->num_sms = prop.multiProcessorCount;
+  ex->win_bytes = static_cast<size_t>(round_up(2ll * world * max_nq * max_k * 8, 256));
+  ex->total_bytes = ex->win_bytes + static_cast<size_t>(round_up(2ll * world * max_nq * 4, 256));
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, ex->total_bytes);
+  if (e != cudaSuccess) {
+    delete ex;
+    return fail(VFI_ERR_NOMEM, std::string("cudaMalloc(exchange window): ") + cudaGetErrorString(e));
+  }
+  ex->local = static_cast<uint8_t*>(p);
+  ex->peer[rank] = ex->local;
+  e = cudaMemset(p, 0, ex->total_bytes);          // flags start at epoch 0; synchronous w.r.t. the host
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  int occ = 1;
+  if (e == cudaSuccess)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vfi::exchange_merge_kernel, 256, sizeof(vfi::SelectSmem));
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    delete ex;
+    return fail(VFI_ERR_CUDA, std::string("exchange window setup: ") + cudaGetErrorString(e));
+  }
+  ex->max_resident = std::max(1, occ) * ex->num_sms;   // the grid never exceeds what is resident at once
+  ex->connected = (world == 1);
+  *out = ex;
+  return VFI_OK;
+}
+
+int vfi_exchange_handle(vfi_exchange_t* ex, void* out_handle) {
+  if (!ex || !out_handle) return fail(VFI_ERR_INVALID, "bad argument to vfi_exchange_handle");
+  static_assert(sizeof(cudaIpcMemHandle_t) == VFI_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  DeviceGuard guard(ex->device);
+  cudaIpcMemHandle_t h;
+  VFI_CUDA(cudaIpcGetMemHandle(&h, ex->local));
+  std::memcpy(out_handle, &h, sizeof(h));
+  return VFI_OK;
+}
+
+int vfi_exchange_connect(vfi_exchange_t* ex, const void* handles) {
+  if (!ex || !handles) return fail(VFI_ERR_INVALID, "bad argument to vfi_exchange_connect");
+  std::lock_guard<std::mutex> lock(ex->mu);
+  if (ex->connected) return VFI_OK;
+  DeviceGuard guard(ex->device);
+  const uint8_t* hb = static_cast<const uint8_t*>(handles);
+  for (int r = 0; r < ex->world; ++r) {
+    if (r == ex->rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, hb + static_cast<size_t>(r) * VFI_IPC_HANDLE_BYTES, sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      for (int j = 0; j < r; ++j)
+        if (j != ex->rank && ex->peer[j]) { cudaIpcCloseMemHandle(ex->peer[j]); ex->peer[j] = nullptr; }
+      return fail(VFI_ERR_CUDA, "cudaIpcOpenMemHandle(rank " + std::to_string(r) + "): " + cudaGetErrorString(e) +
+                                    " (peer windows need one process per GPU on one NVLink/PCIe-P2P node)");
+    }
+    ex->peer[r] = static_cast<uint8_t*>(p);
+  }
+  ex->connected = true;
+  return VFI_OK;
+}
+
+int vfi_exchange_set_timeout_ms(vfi_exchange_t* ex, int64_t ms) {
+  if (!ex || ms <= 0) return fail(VFI_ERR_INVALID, "bad argument to vfi_exchange_set_timeout_ms");
+  ex->timeout_ms = static_cast<uint64_t>(ms);
+  return VFI_OK;
+}
+
+int vfi_exchange_merge(vfi_exchange_t* ex, const float* scores, const int64_t* ids, int64_t nq, int k, int k_out,
+                       float* out_scores, int64_t* out_ids, void* stream) {
+  if (!ex || nq < 0 || k <= 0 || k_out <= 0 || (nq > 0 && (!scores || !ids || !out_scores || !out_ids)))
+    return fail(VFI_ERR_INVALID, "bad argument to vfi_exchange_merge");
+  if (!ex->connected) return fail(VFI_ERR_INVALID, "vfi_exchange_merge before vfi_exchange_connect");
+  if (nq > ex->max_nq || k > ex->max_k) return fail(VFI_ERR_INVALID, "nq or k exceeds the window geometry given at create");
+  if (k_out > VFI_MAX_K) return fail(VFI_ERR_UNSUPPORTED, "k_out exceeds VFI_MAX_K");
+  std::lock_guard<std::mutex> lock(ex->mu);
+  DeviceGuard guard(ex->device);
+  if (!guard.ok) return fail(VFI_ERR_CUDA, "cudaSetDevice failed");
+  ex->epoch++;                       // every rank must make the same sequence of calls (a collective)
+  if (nq == 0) return VFI_OK;
+  vfi::ExchangeParams p{};
+  for (int r = 0; r < ex->world; ++r) {
+    p.win[r] = reinterpret_cast<uint64_t*>(ex->peer[r]);
+    p.flags[r] = reinterpret_cast<uint32_t*>(ex->peer[r] + ex->win_bytes);
+  }
+  p.rank = ex->rank;
+  p.world = ex->world;
+  p.nq = static_cast<int>(nq);
+  p.k = k;
+  p.k_out = k_out;
+  p.max_nq = ex->max_nq;
+  p.max_k = ex->max_k;
+  p.epoch = ex->epoch;
+  p.scores = scores;
+  p.ids = ids;
+  p.out_scores = out_scores;
+  p.out_ids = out_ids;
+  p.timeout_ns = ex->timeout_ms * 1000000ull;
+  const int grid = static_cast<int>(std::min<int64_t>(nq, ex->max_resident));
+  vfi::exchange_merge_kernel<<<grid, 256, sizeof(vfi::SelectSmem), static_cast<cudaStream_t>(stream)>>>(p);
+  LAUNCHED();
+  VFI_CUDA(cudaGetLastError());
+  return VFI_OK;
+}
+
+int vfi_exchange_destroy(vfi_exchange_t* ex) {
+  if (!ex) return VFI_OK;
+  DeviceGuard guard(ex->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < ex->world; ++r)
+    if (r != ex->rank && ex->peer[r]) cudaIpcCloseMemHandle(ex->peer[r]);
+  if (ex->local) cudaFree(ex->local);
+  cudaGetLastError();
+  delete ex;
   return VFI_OK;
 }
 

@@ -6,6 +6,12 @@ exchange is one all-gather of the packed per-rank result [B,k] x (fp32 score, in
 the merge kernel (K3) on every rank.  Scores are the canonical rescored values, so the sharded result
 is bit-identical to the single-GPU result for any G.
 
+On NVLink boxes the exchange and the merge are ONE kernel per rank over peer memory (`PeerExchange`,
+csrc/peer_exchange.cuh): every rank stores its results straight into windows in its peers' HBM, signals per-query
+flags and merges what it received — no pack/unpack kernels and no NCCL launch on the data path (NCCL is only used
+once, to hand round the 64-byte IPC handles).  The all-gather route stays as the portable path (gloo on CPU, or
+VFI_EXCHANGE=nccl).
+
 The reference has no counterpart (workers are replicas: /root/reference/experiments/retriever/step3_mul.py:405-446).
 On CPU (gloo) the class is exercised with an injected local searcher; the product path needs CUDA."""
 from __future__ import annotations
@@ -36,16 +42,67 @@ def unpack(buf: torch.Tensor, k: int):
     return scores, ids
 
 
+class PeerExchange:
+    """Receive windows in every rank's HBM, mapped by all peers through CUDA IPC (include/vfi.h: vfi_exchange_*).
+
+    `merge(scores, ids, k_out)` is a collective: every rank calls it with its own [B,k] shard result and gets the
+    global top-k_out, bit-identical on all ranks.  Global ids must be < 2^32 - 1."""
+
+    def __init__(self, device: torch.device, max_nq: int, max_k: int, group=None):
+        import ctypes as C
+
+        from . import _native as N
+        self._N, self._C = N, C
+        self.device = device
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.max_nq, self.max_k = int(max_nq), int(max_k)
+        self._h = C.c_void_p()
+        lib = N.load()
+        N.check(lib.vfi_exchange_create(device.index or 0, self.rank, self.world, self.max_nq, self.max_k, C.byref(self._h)))
+        mine = (C.c_uint8 * N.IPC_HANDLE_BYTES)()
+        N.check(lib.vfi_exchange_handle(self._h, mine))
+        # the handles travel once over whatever backend the group has (NCCL here); the data path never uses it
+        t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=device)
+        allh = torch.empty(self.world * N.IPC_HANDLE_BYTES, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, t, group=group)
+        buf = (C.c_uint8 * (self.world * N.IPC_HANDLE_BYTES)).from_buffer_copy(bytes(allh.cpu().numpy().tobytes()))
+        N.check(lib.vfi_exchange_connect(self._h, buf))
+        dist.barrier(group=group)       # every window is zeroed and mapped before the first push
+
+    def merge(self, scores: torch.Tensor, ids: torch.Tensor, k_out: int):
+        C, N = self._C, self._N
+        B, k = scores.shape
+        scores, ids = scores.contiguous(), ids.contiguous()
+        out_s = torch.empty((B, k_out), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((B, k_out), dtype=torch.int64, device=self.device)
+        N.check(N.load().vfi_exchange_merge(self._h, C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()), B, k, int(k_out),
+                                            C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()),
+                                            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return out_i, out_s
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            torch.cuda.synchronize(self.device)
+            if dist.is_initialized():
+                dist.barrier(group=self.group)   # no peer is still storing into a window that is about to be freed
+            self._N.load().vfi_exchange_destroy(self._h)
+            self._h = self._C.c_void_p()
+
+
 class ShardedSearcher:
-    """all-gather + merge around any local searcher `local(q, k) -> (ids [B,k], scores [B,k])`.
+    """exchange + merge around any local searcher `local(q, k) -> (ids [B,k], scores [B,k])`.
 
     merge: callable (scores [G,B,k], ids [G,B,k], k) -> (ids [B,k], scores [B,k]); the CUDA merge kernel in
-    production (veritasfi_b200.dense.merge_topk)."""
+    production (veritasfi_b200.dense.merge_topk).  exchange: a PeerExchange (fused push + merge over NVLink peer
+    memory) or None (all-gather over the process group, then `merge`)."""
 
-    def __init__(self, local: Callable, merge: Callable, group=None):
+    def __init__(self, local: Callable, merge: Callable, group=None, exchange: "PeerExchange | None" = None):
         self.local = local
         self.merge = merge
         self.group = group
+        self.exchange = exchange
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
@@ -53,6 +110,8 @@ class ShardedSearcher:
         ids, scores = self.local(q, k)
         if self.world == 1:
             return ids, scores
+        if self.exchange is not None and scores.shape[0] <= self.exchange.max_nq and k <= self.exchange.max_k:
+            return self.exchange.merge(scores, ids, k)
         mine = pack(scores, ids)
         flat = torch.empty((self.world * mine.shape[0], mine.shape[1]), dtype=mine.dtype, device=mine.device)
         dist.all_gather_into_tensor(flat, mine, group=self.group)     # rank-major concatenation along dim 0
@@ -60,9 +119,20 @@ class ShardedSearcher:
         return self.merge(g_scores, g_ids, k)
 
 
-def make_sharded_dense(index, group=None) -> ShardedSearcher:
-    """Production wiring: local = DenseIndex.search_batch on this rank's shard, merge = K3 on the GPU."""
+def make_sharded_dense(index, group=None, exchange: str | None = None, max_nq: int = 1024, max_k: int = 256) -> ShardedSearcher:
+    """Production wiring: local = DenseIndex.search_batch on this rank's shard, merge = K3 on the GPU.
+
+    exchange: "peer" (fused push + merge kernel over NVLink peer memory), "nccl" (all-gather + merge kernel), or None =
+    the VFI_EXCHANGE environment variable, default "peer"."""
+    import os
+
     from .dense import merge_topk
 
+    mode = (exchange or os.environ.get("VFI_EXCHANGE", "peer")).lower()
+    if mode not in ("peer", "nccl"):
+        raise ValueError("exchange must be 'peer' or 'nccl'")
+    ex = None
+    if mode == "peer" and dist.is_initialized() and dist.get_world_size(group) > 1:
+        ex = PeerExchange(index.device, max_nq, max_k, group)
     return ShardedSearcher(lambda q, k: index.search_batch(q, k),
-                           lambda s, i, k: merge_topk(s, i, k), group)
+                           lambda s, i, k: merge_topk(s, i, k), group, ex)
