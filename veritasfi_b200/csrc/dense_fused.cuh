@@ -59,6 +59,52 @@ struct DenseParams {
   int cluster;            // CTAs per cluster (1, 2, 4 or 8; divides n_mtiles): they share each corpus tile by TMA multicast
 };
 
+// One 32-column chunk of one query's scores against its admission threshold: admitted (score, id) keys are
+// appended to the query's buffer; a buffer that cannot take another 32 keys is compacted to the exact k' best by
+// its warp (warp_select_compact) and the threshold rises.  All 32 lanes must call.
+__device__ __forceinline__ void admit_chunk(const float (&v)[32], uint32_t id0, uint32_t n_rows, bool valid_q, float& tau_f,
+                                            uint64_t& tau_key, uint32_t& count, uint64_t* buf, int cap, int keep,
+                                            uint32_t* my_hist, uint32_t lane) {
+  // group maxima (4 columns each) feed both the chunk test and the per-group tests
+  float m4[8];
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    m4[g] = fmaxf(fmaxf(v[4 * g], v[4 * g + 1]), fmaxf(v[4 * g + 2], v[4 * g + 3]));
+  const float mx = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])),
+                         fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
+  if (valid_q && mx >= tau_f) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (m4[g] >= tau_f) {
+#pragma unroll
+        for (int j = 4 * g; j < 4 * g + 4; ++j) {
+          if (v[j] >= tau_f && id0 + j < n_rows) {
+            const uint64_t key = make_key(v[j], id0 + j);
+            if (key > tau_key) buf[count++] = key;
+          }
+        }
+      }
+    }
+  }
+  // a buffer that cannot take another 32 keys is compacted now (warp-cooperative)
+  uint32_t need = __ballot_sync(0xFFFFFFFFu, count + 32 > static_cast<uint32_t>(cap));
+  while (need) {
+    const uint32_t src = __ffs(need) - 1;
+    need &= need - 1;
+    uint64_t* sbuf = reinterpret_cast<uint64_t*>(
+        __shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(buf), src));
+    const uint32_t sn = __shfl_sync(0xFFFFFFFFu, count, src);
+    __syncwarp();
+    const uint64_t kth = warp_select_compact(sbuf, sn, keep, my_hist, lane);
+    if (lane == src) {
+      count = keep;
+      tau_key = kth;
+      tau_f = key_score(kth);
+    }
+    __syncwarp();
+  }
+}
+
 // ===================== epilogue: TMEM -> registers -> threshold filter =====================
 // Run by warps 4..11 of a CTA.  Two warp sets: set 0 (warps 4-7) drains accumulator stage 0 = the even tiles of
 // this CTA, set 1 (warps 8-11) stage 1 = the odd tiles, so two tiles are filtered concurrently.  Each set keeps
@@ -110,45 +156,8 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t tm
             dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
       } else {
-        // group maxima (4 columns each) feed both the chunk test and the per-group tests
-        float m4[8];
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          m4[g] = fmaxf(fmaxf(v[4 * g], v[4 * g + 1]), fmaxf(v[4 * g + 2], v[4 * g + 3]));
-        const float mx = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])),
-                               fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
-        if (valid_q && mx >= tau_f) {
-          const uint32_t id0 = row0 + c * 32;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (m4[g] >= tau_f) {
-#pragma unroll
-              for (int j = 4 * g; j < 4 * g + 4; ++j) {
-                if (v[j] >= tau_f && id0 + j < static_cast<uint32_t>(p.n_rows)) {
-                  const uint64_t key = make_key(v[j], id0 + j);
-                  if (key > tau_key) buf[count++] = key;
-                }
-              }
-            }
-          }
-        }
-        // a buffer that cannot take another 32 keys is compacted now (warp-cooperative)
-        uint32_t need = __ballot_sync(0xFFFFFFFFu, count + 32 > static_cast<uint32_t>(p.cap));
-        while (need) {
-          const uint32_t src = __ffs(need) - 1;
-          need &= need - 1;
-          uint64_t* sbuf = reinterpret_cast<uint64_t*>(
-              __shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(buf), src));
-          const uint32_t sn = __shfl_sync(0xFFFFFFFFu, count, src);
-          __syncwarp();
-          const uint64_t kth = warp_select_compact(sbuf, sn, p.keep, my_hist, lane);
-          if (lane == src) {
-            count = p.keep;
-            tau_key = kth;
-            tau_f = key_score(kth);
-          }
-          __syncwarp();
-        }
+        admit_chunk(v, row0 + c * 32, static_cast<uint32_t>(p.n_rows), valid_q, tau_f, tau_key, count, buf, p.cap, p.keep,
+                    my_hist, lane);
       }
     }
     ptx::tc_fence_before();
@@ -284,14 +293,32 @@ dense_fused_kernel(const __grid_constant__ CUtensorMap tmap_q,
 // CTA and corpus tile) and the shared-memory operand reads per MMA from 12 KB to 8 KB.  Measured reason: under
 // the 1 kW power cap the single-CTA kernel drops the SM clock to ~960-1140 MHz where cuBLAS holds ~1335 MHz on the
 // same box (profiles/): the fill traffic, not the MMA, was the power hog.
+//
+// Work decomposition: pair c owns the corpus tiles c, c+P, c+2P .. (P pairs) and, for each of them, walks ALL query
+// tile pairs (mp = 0 .. n_mtiles/2-1) before moving on.  A corpus tile is therefore requested by one TPC only: it
+// leaves HBM once and its re-reads hit the L2 of that TPC's die.  (With several pairs per tile, requests from the
+// two dies arrived far enough apart that every tile was fetched from HBM twice — ncu: 41 GB for a 20.5 GB corpus.)
+// Every SM pair of the chip is busy for any batch size.  Per-query selection state (count, threshold) lives in
+// shared memory between the visits of a query tile.
+//
 // Barriers: full[s] lives in the leader and counts the TMA bytes of BOTH CTAs; empty[s] and tfull[a] exist in both
 // CTAs and are signalled by one multicast tcgen05.commit; tempty[a] lives in the leader and collects the 8 epilogue
 // warps of the pair (the peer's arrive remotely).
 // ==================================================================================================
 constexpr int kPairStages = 6;
 constexpr int kPairBBytes = (kBN / 2) * kBK * 2;   // 16 KB: this CTA's half of the corpus tile
-constexpr int kPairSmemBytes =
-    1024 /*align slack*/ + kPairStages * (kABytes + kPairBBytes) + 256 /*barriers*/ + 8 * 256 * 4 /*hist*/;
+constexpr int kPairMaxMp = 4;                       // query tile pairs per launch (1024 queries)
+struct PairSelState {                               // [epilogue set][query tile pair][thread of the set]
+  uint64_t tau_key[2][kPairMaxMp][128];
+  float tau_f[2][kPairMaxMp][128];
+  uint32_t count[2][kPairMaxMp][128];
+};
+constexpr int kPairSmemBytes = 1024 /*align slack*/ + kPairStages * (kABytes + kPairBBytes) + 256 /*barriers*/ +
+                               8 * 256 * 4 /*hist*/ + static_cast<int>(sizeof(PairSelState));
+
+// buffers per query in MODE_TOPK: one per pair when every query tile pair is always drained by the same epilogue set
+// (even number of tile pairs), else one per (pair, set)
+__host__ __device__ inline int pair_sets_per_query(int n_mtiles) { return ((n_mtiles / 2) % 2 == 0) ? 1 : 2; }
 
 template <int MODE>
 __global__ void __launch_bounds__(kDenseThreads, 1)
@@ -309,6 +336,7 @@ dense_fused_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
   uint64_t* tempty_bar = bars + 2 * kPairStages + 2;  // [2]            epilogues of the pair -> MMA (leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairStages + 4);
   uint32_t* hist = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  PairSelState* sel = reinterpret_cast<PairSelState*>(reinterpret_cast<uint8_t*>(hist) + 8 * 256 * 4);
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -341,56 +369,136 @@ dense_fused_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t tmem_base = *tmem_slot;
 
   const int pair = static_cast<int>(blockIdx.x) >> 1;
-  const int n_mpairs = p.n_mtiles >> 1;
-  const int m_tile = (pair % n_mpairs) * 2 + static_cast<int>(crank);
-  const int group = pair / n_mpairs;
-  const bool active = group < p.n_groups;
+  const int n_pairs = p.n_groups;                     // pairs that own corpus tiles (every launched pair)
+  const int n_mp = p.n_mtiles >> 1;
   const int nkb = p.n_kblocks;
 
-  if (active && warp == 0 && lane == 0) {
+  if (warp == 0 && lane == 0) {
     // ===================== TMA producer (one per CTA) =====================
     uint32_t stage = 0, phase = 0;
-    const uint64_t d_hint = (p.n_mtiles > 2) ? ptx::kEvictNormal : ptx::kEvictFirst;
-    for (int t = group; t < p.n_tiles; t += p.n_groups) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-        const uint32_t full_leader = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0u);
-        if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * (kABytes + kPairBBytes));
-        ptx::tma_load_2d_pair(sA + stage * kABytes, &tmap_q, full_leader, kb * kBK, m_tile * kBM, ptx::kEvictLast);
-        ptx::tma_load_2d_pair(sB + stage * kPairBBytes, &tmap_d, full_leader, kb * kBK,
-                              t * kBN + static_cast<int>(crank) * (kBN / 2), d_hint);
-        if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+    for (int t = pair; t < p.n_tiles; t += n_pairs) {
+      for (int mp = 0; mp < n_mp; ++mp) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t full_leader = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0u);
+          if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * (kABytes + kPairBBytes));
+          ptx::tma_load_2d_pair(sA + stage * kABytes, &tmap_q, full_leader, kb * kBK, (2 * mp + static_cast<int>(crank)) * kBM,
+                                ptx::kEvictLast);
+          // the first visit of a tile streams it from HBM, the other n_mp-1 find it in this die's L2
+          ptx::tma_load_2d_pair(sB + stage * kPairBBytes, &tmap_d, full_leader, kb * kBK,
+                                t * kBN + static_cast<int>(crank) * (kBN / 2), mp == n_mp - 1 ? ptx::kEvictFirst : ptx::kEvictNormal);
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
       }
     }
-  } else if (active && leader && warp == 1 && lane == 0) {
+  } else if (leader && warp == 1 && lane == 0) {
     // ===================== MMA issuer (one thread of the leader CTA) =====================
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * kBM, kBN);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    for (int t = group; t < p.n_tiles; t += p.n_groups) {
-      ptx::mbar_wait_cluster_acquire(&tempty_bar[acc], acc_phase ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * kBN;
-      for (int kb = 0; kb < nkb; ++kb) {
-        ptx::mbar_wait(&full_bar[stage], phase);
+    for (int t = pair; t < p.n_tiles; t += n_pairs) {
+      for (int mp = 0; mp < n_mp; ++mp) {
+        ptx::mbar_wait_cluster_acquire(&tempty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
-        const uint32_t a_addr = ptx::smem_u32(sA + stage * kABytes);
-        const uint32_t b_addr = ptx::smem_u32(sB + stage * kPairBBytes);
+        const uint32_t d_tmem = tmem_base + acc * kBN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(sA + stage * kABytes);
+          const uint32_t b_addr = ptx::smem_u32(sB + stage * kPairBBytes);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          ptx::umma_bf16_ss_pair(d_tmem, ptx::umma_desc_k128(a_addr + k * 32), ptx::umma_desc_k128(b_addr + k * 32),
-                                 idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) {
+            ptx::umma_bf16_ss_pair(d_tmem, ptx::umma_desc_k128(a_addr + k * 32), ptx::umma_desc_k128(b_addr + k * 32),
+                                   idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::tc_commit_pair_mcast(&empty_bar[stage], 3);            // frees the stage in both CTAs when the MMAs retire
+          if (kb == nkb - 1) ptx::tc_commit_pair_mcast(&tfull_bar[acc], 3);   // accumulator complete, both epilogues
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
         }
-        ptx::tc_commit_pair_mcast(&empty_bar[stage], 3);            // frees the stage in both CTAs when the MMAs retire
-        if (kb == nkb - 1) ptx::tc_commit_pair_mcast(&tfull_bar[acc], 3);   // accumulator complete, both epilogues
-        if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
-  } else if (active && warp >= 4) {
-    const uint32_t tempty_leader = ptx::mapa_u32(ptx::smem_u32(&tempty_bar[0]), 0u);
-    dense_epilogue<MODE>(p, tmem_base, warp, lane, m_tile, group, tfull_bar, hist,
-                         [&](uint32_t a) { ptx::mbar_arrive_cluster(tempty_leader + a * 8u); });
+  } else if (warp >= 4) {
+    // ===================== epilogue: set 0 (warps 4-7) drains accumulator 0 = the even work items (tile, mp) of this
+    // pair, set 1 (warps 8-11) accumulator 1 = the odd ones =====================
+    const uint32_t set = (warp - 4) >> 2;
+    const uint32_t wq = (warp - 4) & 3;               // TMEM lane quadrant of this warp (= warp % 4)
+    const uint32_t tq = wq * 32 + lane;               // thread of the set = TMEM lane = query within the tile
+    uint32_t* my_hist = hist + (warp - 4) * 256;
+    const uint32_t tempty_leader = ptx::mapa_u32(ptx::smem_u32(&tempty_bar[set]), 0u);
+    const int nspq = pair_sets_per_query(p.n_mtiles);
+    if (MODE == MODE_TOPK) {
+      for (int mp = 0; mp < n_mp; ++mp) {
+        const int qi = (2 * mp + static_cast<int>(crank)) * kBM + static_cast<int>(tq);
+        float tf = -INFINITY;
+        uint64_t tk = kKeyNone;
+        if (qi < p.nq && p.tau_init != nullptr) {
+          tf = p.tau_init[qi];
+          tk = make_key(tf, 0u);                      // admits score > hint only
+        }
+        sel->tau_f[set][mp][tq] = tf;
+        sel->tau_key[set][mp][tq] = tk;
+        sel->count[set][mp][tq] = 0u;
+      }
+    }
+    uint32_t acc_phase = 0;
+    int item = 0;
+    for (int t = pair; t < p.n_tiles; t += n_pairs) {
+      for (int mp = 0; mp < n_mp; ++mp, ++item) {
+        if ((item & 1) != static_cast<int>(set)) continue;
+        const int qi = (2 * mp + static_cast<int>(crank)) * kBM + static_cast<int>(tq);
+        const bool valid_q = qi < p.nq;
+        uint64_t* buf = nullptr;
+        uint32_t count = 0;
+        uint64_t tau_key = kKeyNone;
+        float tau_f = -INFINITY;
+        if (MODE == MODE_TOPK) {
+          const size_t slot = (static_cast<size_t>(pair) * nspq + (nspq == 2 ? set : 0u)) * p.nq_pad + qi;
+          buf = p.cand + slot * p.cap;
+          count = sel->count[set][mp][tq];
+          tau_key = sel->tau_key[set][mp][tq];
+          tau_f = sel->tau_f[set][mp][tq];
+        }
+        ptx::mbar_wait(&tfull_bar[set], acc_phase);
+        acc_phase ^= 1;
+        ptx::tc_fence_after();
+        const uint32_t row0 = static_cast<uint32_t>(t) * kBN;
+        const uint32_t taddr = tmem_base + ((wq * 32u) << 16) + set * kBN;
+#pragma unroll 1
+        for (int c = 0; c < kBN / 32; ++c) {
+          float v[32];
+          ptx::tmem_ld_32x32(taddr + c * 32, v);
+          ptx::tmem_ld_wait();
+          if (MODE == MODE_STORE) {
+            if (valid_q) {
+              float4* dst = reinterpret_cast<float4*>(p.scores_out + static_cast<size_t>(qi) * p.ld_scores + row0 + c * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          } else {
+            admit_chunk(v, row0 + c * 32, static_cast<uint32_t>(p.n_rows), valid_q, tau_f, tau_key, count, buf, p.cap, p.keep,
+                        my_hist, lane);
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader);
+        if (MODE == MODE_TOPK) {
+          sel->count[set][mp][tq] = count;
+          sel->tau_key[set][mp][tq] = tau_key;
+          sel->tau_f[set][mp][tq] = tau_f;
+        }
+      }
+    }
+    if (MODE == MODE_TOPK) {
+      // publish the counts of the buffers this set owns (untouched ones hold 0)
+      for (int mp = 0; mp < n_mp; ++mp) {
+        if (nspq == 1 && (mp & 1) != static_cast<int>(set)) continue;
+        const int qi = (2 * mp + static_cast<int>(crank)) * kBM + static_cast<int>(tq);
+        const size_t slot = (static_cast<size_t>(pair) * nspq + (nspq == 2 ? set : 0u)) * p.nq_pad + qi;
+        p.cand_count[slot] = (qi < p.nq) ? sel->count[set][mp][tq] : 0u;
+      }
+    }
   }
 
   // teardown: nobody leaves while the peer can still signal its barriers or read its shared memory

@@ -217,6 +217,7 @@ struct vfi_index {
   int64_t n = 0, cap_rows = 0;
   int64_t id_offset = 0;
   int num_sms = 148;
+  int max_pairs = 0;       // co-resident 2-CTA clusters of the pair kernel (queried once)
   uint16_t* g = nullptr;   // [cap_rows][kp] bf16 gemm operand rows
   float* master = nullptr; // [cap_rows][dp] fp32 rows (F32 store only)
   uint32_t* xnorm_bits = nullptr;
@@ -544,6 +545,30 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
   const int n_tiles = static_cast<int>(ceil_div(n_rows, vfi::kBN));
   int n_groups = std::max(1, n_ctas / n_mtiles);
   n_groups = std::min(n_groups, std::max(1, n_tiles));
+  // pair kernel: every SM pair owns corpus tiles (n_groups = number of pairs) and walks all query tile pairs itself
+  if (pair) {
+    if (idx->max_pairs <= 0) {   // how many 2-CTA clusters of this kernel the device holds at once (74 on a full B200)
+      cudaLaunchConfig_t oc{};
+      oc.gridDim = dim3(static_cast<unsigned>(idx->num_sms));
+      oc.blockDim = dim3(vfi::kDenseThreads);
+      oc.dynamicSmemBytes = vfi::kPairSmemBytes;
+      cudaLaunchAttribute oa[1];
+      oa[0].id = cudaLaunchAttributeClusterDimension;
+      oa[0].val.clusterDim.x = 2;
+      oa[0].val.clusterDim.y = 1;
+      oa[0].val.clusterDim.z = 1;
+      oc.attrs = oa;
+      oc.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, vfi::dense_fused_pair_kernel<vfi::MODE_TOPK>, &oc) != cudaSuccess || nc <= 0) {
+        cudaGetLastError();
+        nc = idx->num_sms / 2;
+      }
+      idx->max_pairs = nc;
+    }
+    n_groups = std::max(1, std::min(std::min(n_ctas / 2, idx->max_pairs), std::max(1, n_tiles)));
+  }
+  const int n_bufs = pair ? n_groups * vfi::pair_sets_per_query(n_mtiles) : 2 * n_groups;   // key buffers per query
   const int nq_pad = n_mtiles * vfi::kBM;
   const int cap = 2 * keep + 32;
   CUtensorMap tq, td;
@@ -568,14 +593,14 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
   p.ld_scores = ld_scores;
   p.cluster = cluster;
   if (mode == vfi::MODE_TOPK) {
-    VFI_TRY(idx->w_cand.ensure(static_cast<size_t>(2 * n_groups) * nq_pad * cap * 8));
-    VFI_TRY(idx->w_cand_count.ensure(static_cast<size_t>(2 * n_groups) * nq_pad * 4));
+    VFI_TRY(idx->w_cand.ensure(static_cast<size_t>(n_bufs) * nq_pad * cap * 8));
+    VFI_TRY(idx->w_cand_count.ensure(static_cast<size_t>(n_bufs) * nq_pad * 4));
     p.cand = idx->w_cand.as<uint64_t>();
     p.cand_count = idx->w_cand_count.as<uint32_t>();
   }
   const bool prof = idx->opt_profile != 0 && profile;
   if (prof) cudaEventRecord(idx->ev0, st);
-  const int grid = n_groups * n_mtiles;
+  const int grid = pair ? 2 * n_groups : n_groups * n_mtiles;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(vfi::kDenseThreads);
@@ -599,7 +624,7 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
   if (prof) cudaEventRecord(idx->ev1, st);
   VFI_CUDA(cudaGetLastError());
   if (profile) idx->stats.fused_launches++;
-  if (o_groups) *o_groups = 2 * n_groups;   // one key buffer per (group, epilogue set)
+  if (o_groups) *o_groups = n_bufs;
   if (o_nq_pad) *o_nq_pad = nq_pad;
   if (o_cap) *o_cap = cap;
   return VFI_OK;
