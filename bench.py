@@ -132,6 +132,8 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=250_000, help="rows of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hint", type=int, default=1)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: fused peer-memory push+merge kernel over NVLink, or NCCL all-gather + merge kernel")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
@@ -139,7 +141,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     steps, warmup = max(1, args.steps), max(3, args.warmup) if args.impl == "b200" else max(0, args.warmup)
     config = {"workload": f"{args.workload}: {w['desc']}", "corpus_rows": w["n"], "dim": w["d"], "batch": w["b"], "k": w["k"],
-              "sharding": f"row-sharded over {world} GPU(s)", "l2": "inputs exceed L2 (corpus shard >> 126 MB); no flush needed"}
+              "sharding": f"row-sharded over {world} GPU(s)" + (f", exchange={args.exchange}" if world > 1 else ""), "l2": "inputs exceed L2 (corpus shard >> 126 MB); no flush needed"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -180,7 +182,7 @@ def main():
     torch.cuda.synchronize()
     index.set_option(N.OPT_TAU_HINT, args.hint)
     index.set_option(N.OPT_PROFILE, 1)
-    searcher = make_sharded_dense(index)
+    searcher = make_sharded_dense(index, exchange=args.exchange, max_nq=w["b"], max_k=w["k"])
     q_dev = synth.dense_queries_torch(w["b"], w["d"], SEED, dev)
     q_pin = torch.empty((w["b"], w["d"]), dtype=torch.float32).pin_memory()
     q_pin.copy_(q_dev.cpu())

@@ -24,19 +24,6 @@ __device__ __forceinline__ float bf16_to_f32(uint16_t h) {
   return __uint_as_float(static_cast<uint32_t>(h) << 16);
 }
 
-// fp32 bit pattern -> the same value as fp64 with integer ops only (fp64 conversions share the slow
-// fp64 pipe with the DFMA chain).  Normal numbers: sign | (exponent + 896) << 52 | mantissa << 29;
-// zero maps to zero.  Denormals / inf / NaN are not representable this way: `odd` collects a flag and
-// the caller redoes the batch with the conversion instruction (never taken on real embeddings).
-__device__ __forceinline__ double widen_f32_bits(uint32_t f, uint32_t& odd) {
-  const uint32_t e = f & 0x7F800000u;
-  const uint32_t hi_n = (f & 0x80000000u) | (((f & 0x7FFFFFFFu) >> 3) + 0x38000000u);
-  const uint32_t hi = (e != 0u) ? hi_n : (f & 0x80000000u);
-  const uint32_t lo = (e != 0u) ? (f << 29) : 0u;
-  odd |= (e == 0x7F800000u) | ((e == 0u) & ((f & 0x007FFFFFu) != 0u));
-  return __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
-}
-
 // butterfly (xor 16,8,4,2,1) sum in fp64 — the fixed order the oracle restates for norms
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
@@ -270,6 +257,9 @@ struct CanonCfg {
 
 // Canonical scores of 32 rows against one query: lane l owns row `id` (valid or not).  my_tile: 32*kCanonPitch
 // words, my_qs: CanonCfg<RowT>::kElems doubles, both private to the calling warp.  All 32 lanes must call.
+// Measured on B200 (profiles/r1_tail_conv.md): vector fp64 issues at ~2 lanes/clk/SM, so the DFMA chain is the
+// floor of this routine (16 SM-cycles per warp-wide DFMA); widening the stored values with integer instructions
+// instead of F2F.F64.F32 cost 17 ALU instructions per element and was slower (300 vs 232 us for 1024 x 128 rows).
 template <typename RowT>
 __device__ __forceinline__ float canon_dot_warp(const RowT* __restrict__ rows, int64_t row_pitch, int dp,
                                                 const float* __restrict__ qv, uint32_t id, bool valid,
@@ -308,43 +298,31 @@ __device__ __forceinline__ float canon_dot_warp(const RowT* __restrict__ rows, i
     __syncwarp();
     if (c0 + kElems < dp) fetch(c0 + kElems);          // next chunk in flight while this one is summed
     const uint32_t* mine = my_tile + lane * kCanonPitch;
-    // batches of 8 words: all shared loads and widenings first, then the dependent fp64 chain
-#pragma unroll 1
-    for (int w0 = 0; w0 < kCanonWords; w0 += 8) {
-      uint32_t u[8];
+    // batches of 4 words: conversions are independent of the chain, so they issue ahead of it
+#pragma unroll 2
+    for (int w0 = 0; w0 < kCanonWords; w0 += 4) {
+      uint32_t u[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) u[i] = mine[w0 + i];
-      uint32_t odd = 0;
+      for (int i = 0; i < 4; ++i) u[i] = mine[w0 + i];
       if (sizeof(RowT) == 2) {
-        double xd[16], qd[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) qd[i] = my_qs[2 * w0 + i];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          xd[2 * i] = widen_f32_bits(u[i] << 16, odd);
-          xd[2 * i + 1] = widen_f32_bits(u[i] & 0xFFFF0000u, odd);
-        }
-        if (odd) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            xd[2 * i] = static_cast<double>(__uint_as_float(u[i] << 16));
-            xd[2 * i + 1] = static_cast<double>(__uint_as_float(u[i] & 0xFFFF0000u));
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc = fma(qd[i], xd[i], acc);
-      } else {
         double xd[8], qd[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) qd[i] = my_qs[w0 + i];
+        for (int i = 0; i < 8; ++i) qd[i] = my_qs[2 * w0 + i];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) xd[i] = widen_f32_bits(u[i], odd);
-        if (odd) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) xd[i] = static_cast<double>(__uint_as_float(u[i]));
+        for (int i = 0; i < 4; ++i) {
+          xd[2 * i] = static_cast<double>(__uint_as_float(u[i] << 16));
+          xd[2 * i + 1] = static_cast<double>(__uint_as_float(u[i] & 0xFFFF0000u));
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc = fma(qd[i], xd[i], acc);
+      } else {
+        double xd[4], qd[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qd[i] = my_qs[w0 + i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xd[i] = static_cast<double>(__uint_as_float(u[i]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc = fma(qd[i], xd[i], acc);
       }
     }
     __syncwarp();
@@ -486,7 +464,7 @@ struct TailSmem {
 };
 
 template <typename RowT>
-__global__ void __launch_bounds__(256, 2) select_rescore_kernel(
+__global__ void __launch_bounds__(256, 3) select_rescore_kernel(
     const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, int n_groups, int nq_pad, int cap, int keep,
     const float* __restrict__ tau_init, const RowT* __restrict__ rows, int64_t row_pitch, int dp,
     const float* __restrict__ qcanon, int k, int64_t id_offset, const float* __restrict__ eps,
@@ -532,8 +510,8 @@ __global__ void __launch_bounds__(256, 2) select_rescore_kernel(
       uint32_t id = 0;
       float tc = 0.f;
       if (valid) { id = key_id(sm->keys[slot]); tc = key_score(sm->keys[slot]); }
-      const float s = canon_dot_warp<RowT>(rows, row_pitch, dp, qcanon + static_cast<int64_t>(q) * dp, id, valid, ts->tile[warp],
-                                           ts->qs[warp], lane);
+      const float s = canon_dot_warp<RowT>(rows, row_pitch, dp, qcanon + static_cast<int64_t>(q) * dp, id, valid,
+                                                 ts->tile[warp], ts->qs[warp], lane);
       if (valid) {
         keys2[slot] = make_key(s, id);
         if (max_err_bits != nullptr) atomicMax(max_err_bits, __float_as_uint(fabsf(s - tc)));
