@@ -64,10 +64,16 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def wait_first(self, timeout=2.0):
+        t_end = time.time() + timeout
+        while self.proc is not None and not self.rows and time.time() < t_end:
+            time.sleep(0.01)
+        self.mark = len(self.rows)      # samples from here on lie inside (or right at the edge of) the timed region
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -76,11 +82,16 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        mark = getattr(self, "mark", 0)
+        n_end = len(self.rows)
+        if n_end <= mark:               # region shorter than one sampling period: take the next sample
+            time.sleep(0.08)
+            n_end = len(self.rows)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[mark:n_end] or self.rows[-1:]
+        for r in rows:
             parts = [x.strip() for x in r.split(",")]
             if len(parts) < 7:
                 continue
@@ -94,6 +105,16 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def read_traffic(workload: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)[workload]
+        return float(t["dram_bytes_read"] + t["dram_bytes_write"])
+    except Exception:
+        return None
 
 
 def cpu_reference_arm(w, steps: int, warmup: int, rows_sample: int, threads: int | None):
@@ -253,6 +274,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
     launches0 = N.launch_count()
     ms_total = timed(step_device, steps)
     launches = N.launch_count() - launches0
@@ -276,10 +298,12 @@ def main():
         tensor_bound = w["b"] >= 128
         if tensor_bound:
             roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                        "frac": achieved_tf / peaks["tf_sustained"], "traffic": None,
+                        "frac": achieved_tf / peaks["tf_sustained"],
+                        "traffic": read_traffic(args.workload) if world == 1 else None,
                         "kernel": "dense_fused_kernel<MODE_TOPK>", "kernel_ms": kernel_ms,
                         "peak_source": f"{peaks['source']} MEASURED_PEAKS.json bf16_tflops_sustained",
-                        "algorithmic": f"2*B*(N/G)*d = {flops_per_launch:.4g} FLOP per launch"}
+                        "algorithmic": f"2*B*(N/G)*d = {flops_per_launch:.4g} FLOP per launch; (N/G)*d*2 = {float(n_local) * w['d'] * 2:.4g} B",
+                        "traffic_source": "ncu dram__bytes_read+write per launch, profiles/ncu_traffic.json"}
         else:
             bytes_per_launch = float(n_local) * w["d"] * 2
             gbs = bytes_per_launch / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0

@@ -67,6 +67,8 @@ def test_compute_entries_fail_loudly_without_a_device():
     assert (x == 1).all()                       # untouched: nothing ran on the CPU instead
     with pytest.raises(N.NoDeviceError):
         fusion.rrf(np.zeros((1, 2, 3), np.int64), 2)
+    ex = C.c_void_p()
+    assert N.load().vfi_exchange_create(0, 0, 2, 8, 8, C.byref(ex)) == N.ERR_NO_DEVICE   # no CPU stand-in for peer windows
     from veritasfi_b200.bm25_compat import GpuPostings
     with pytest.raises(N.NoDeviceError):
         GpuPostings(np.array([0, 1]), np.array([0], np.int32), np.array([1.0], np.float32), 1)
@@ -81,6 +83,12 @@ def test_argument_validation_happens_before_any_device_work():
     assert lib.vfi_index_create(64, N.STORE_BF16, 0, None) == N.ERR_INVALID
     assert lib.vfi_index_search(None, None, 1, 1, None, None, 0, None) == N.ERR_INVALID
     assert lib.vfi_merge_topk(None, None, 1, 1, 1, 1, None, None, 0, 0, None) == N.ERR_INVALID
+    ex = C.c_void_p()
+    assert lib.vfi_exchange_create(0, 0, 17, 8, 8, C.byref(ex)) == N.ERR_INVALID      # world > 16
+    assert lib.vfi_exchange_create(0, 2, 2, 8, 8, C.byref(ex)) == N.ERR_INVALID       # rank >= world
+    assert lib.vfi_exchange_create(0, 0, 2, 8, N.MAX_K + 1, C.byref(ex)) == N.ERR_INVALID
+    assert lib.vfi_exchange_merge(None, None, None, 1, 1, 1, None, None, None) == N.ERR_INVALID
+    assert lib.vfi_exchange_destroy(None) == N.OK
     assert lib.vfi_index_ntotal(None) == 0
     assert lib.vfi_index_destroy(None) == N.OK
     assert lib.vfi_bm25_destroy(None) == N.OK

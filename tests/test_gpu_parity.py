@@ -113,12 +113,42 @@ def test_admission_hint_does_not_change_results(torch_cuda):
     idx.add(xb)
     q = torch.from_numpy(xq).cuda()
     idx.set_option(N.OPT_FORCE_PATH, N.PATH_FUSED)
+    idx.set_option(N.OPT_TAU_HINT, 0)
     i0, s0 = idx.search_batch(q, 20)
-    idx.set_option(N.OPT_TAU_HINT, 1)
+    idx.set_option(N.OPT_TAU_HINT, 1)            # the library default
     i1, s1 = idx.search_batch(q, 20)
     assert torch.equal(i0, i1) and torch.equal(s0, s1)
     D0, I0 = flat_ip.search(xq, xb, 20)
     assert (i1.cpu().numpy() == I0).all() and (s1.cpu().numpy() == D0).all()
+    idx.close()
+
+
+@pytest.mark.parametrize("nq,pair,hint", [
+    (256, 2, 1),     # one query tile pair: both epilogue sets own a buffer per query
+    (256, 1, 1),     # the same batch on the single-CTA kernel
+    (512, 2, 0),     # two tile pairs, no admission hint: thresholds rise by buffer compaction alone
+    (1024, 2, 1),    # four tile pairs (the benchmark batch)
+    (1000, 0, 1),    # ragged last tile, automatic choice (8 tiles -> pair kernel)
+    (640, 0, 1),     # five tiles (odd) -> automatic fallback to the single-CTA kernel
+])
+def test_cta_pair_kernel_matches_oracle_and_the_single_cta_kernel(torch_cuda, nq, pair, hint):
+    """tcgen05 cta_group::2 path (two SMs share every corpus tile) against the oracle, for every query-tile-pair count."""
+    torch = torch_cuda
+    from oracle import flat_ip
+    from veritasfi_b200 import _native as N
+    from veritasfi_b200.dense import DenseIndex
+    n, d, k = 150_001, 128, 100                      # n not a multiple of 256: ragged last corpus tile
+    xb, xq = _world(n, d, nq, 17, True)
+    idx = DenseIndex(d, store="bf16")
+    idx.add(xb)
+    idx.set_option(N.OPT_FORCE_PATH, N.PATH_FUSED)
+    idx.set_option(N.OPT_CTA_PAIR, pair)
+    idx.set_option(N.OPT_TAU_HINT, hint)
+    ids, scores = idx.search_batch(torch.from_numpy(xq).cuda(), k)
+    D0, I0 = flat_ip.search(xq, xb, k)
+    assert (ids.cpu().numpy() == I0).all()
+    assert (scores.cpu().numpy() == D0).all()
+    assert idx.stats().last_path == N.PATH_FUSED
     idx.close()
 
 

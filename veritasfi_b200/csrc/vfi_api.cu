@@ -223,7 +223,7 @@ struct vfi_index {
   float* master = nullptr; // [cap_rows][dp] fp32 rows (F32 store only)
   uint32_t* xnorm_bits = nullptr;
   // options
-  int64_t opt_overfetch = 0, opt_force_path = 0, opt_profile = 0, opt_tau_hint = 0, opt_num_ctas = 0, opt_cluster = 0, opt_cta_pair = 0;
+  int64_t opt_overfetch = 0, opt_force_path = 0, opt_profile = 0, opt_tau_hint = 1, opt_num_ctas = 0, opt_cluster = 0, opt_cta_pair = 0;
   // workspace
   DevBuf w_qin, w_qcanon, w_qg, w_eps, w_cand, w_cand_count, w_keys, w_keys_n, w_bound, w_keys2, w_flag,
       w_out_scores, w_out_ids, w_stage, w_dbg, w_sel, w_tau;
