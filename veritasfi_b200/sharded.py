@@ -42,6 +42,10 @@ def unpack(buf: torch.Tensor, k: int):
     return scores, ids
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """Raised on EVERY rank when any rank could not set up its peer windows."""
+
+
 class PeerExchange:
     """Receive windows in every rank's HBM, mapped by all peers through CUDA IPC (include/vfi.h: vfi_exchange_*).
 
@@ -60,16 +64,30 @@ class PeerExchange:
         self.max_nq, self.max_k = int(max_nq), int(max_k)
         self._h = C.c_void_p()
         lib = N.load()
-        N.check(lib.vfi_exchange_create(device.index or 0, self.rank, self.world, self.max_nq, self.max_k, C.byref(self._h)))
+        # Local steps may fail on one rank only (no IPC between these processes, out of memory ...); the collectives
+        # below are executed by every rank regardless, and the verdict is shared, so the ranks never diverge.
+        err = None
         mine = (C.c_uint8 * N.IPC_HANDLE_BYTES)()
-        N.check(lib.vfi_exchange_handle(self._h, mine))
+        try:
+            N.check(lib.vfi_exchange_create(device.index or 0, self.rank, self.world, self.max_nq, self.max_k, C.byref(self._h)))
+            N.check(lib.vfi_exchange_handle(self._h, mine))
+        except Exception as e:   # noqa: BLE001
+            err = e
         # the handles travel once over whatever backend the group has (NCCL here); the data path never uses it
         t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=device)
         allh = torch.empty(self.world * N.IPC_HANDLE_BYTES, dtype=torch.uint8, device=device)
         dist.all_gather_into_tensor(allh, t, group=group)
-        buf = (C.c_uint8 * (self.world * N.IPC_HANDLE_BYTES)).from_buffer_copy(bytes(allh.cpu().numpy().tobytes()))
-        N.check(lib.vfi_exchange_connect(self._h, buf))
-        dist.barrier(group=group)       # every window is zeroed and mapped before the first push
+        if err is None:
+            try:
+                buf = (C.c_uint8 * (self.world * N.IPC_HANDLE_BYTES)).from_buffer_copy(bytes(allh.cpu().numpy().tobytes()))
+                N.check(lib.vfi_exchange_connect(self._h, buf))
+            except Exception as e:   # noqa: BLE001
+                err = e
+        bad = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)   # also the barrier: every window is zeroed and mapped
+        if int(bad.item()):
+            self.close(barrier=False)     # the all-reduce above already ordered every rank; nobody has pushed yet
+            raise PeerExchangeUnavailable(str(err) if err is not None else "setup failed on another rank")
 
     def merge(self, scores: torch.Tensor, ids: torch.Tensor, k_out: int):
         C, N = self._C, self._N
@@ -82,10 +100,10 @@ class PeerExchange:
                                             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         return out_i, out_s
 
-    def close(self) -> None:
+    def close(self, barrier: bool = True) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
             torch.cuda.synchronize(self.device)
-            if dist.is_initialized():
+            if barrier and dist.is_initialized():
                 dist.barrier(group=self.group)   # no peer is still storing into a window that is about to be freed
             self._N.load().vfi_exchange_destroy(self._h)
             self._h = self._C.c_void_p()
@@ -133,6 +151,12 @@ def make_sharded_dense(index, group=None, exchange: str | None = None, max_nq: i
         raise ValueError("exchange must be 'peer' or 'nccl'")
     ex = None
     if mode == "peer" and dist.is_initialized() and dist.get_world_size(group) > 1:
-        ex = PeerExchange(index.device, max_nq, max_k, group)
+        # peer windows need CUDA IPC between the ranks' processes; if any rank cannot map its peers every rank falls
+        # back to the all-gather route together (PeerExchange shares the verdict, so the ranks never disagree)
+        try:
+            ex = PeerExchange(index.device, max_nq, max_k, group)
+        except PeerExchangeUnavailable as e:
+            import warnings
+            warnings.warn(f"peer-memory exchange unavailable ({e}); using the NCCL all-gather route")
     return ShardedSearcher(lambda q, k: index.search_batch(q, k),
                            lambda s, i, k: merge_topk(s, i, k), group, ex)
