@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=250_000, help="rows of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hint", type=int, default=1)
+    ap.add_argument("--tail", type=int, default=0, help="VFI_OPT_TAIL (0 default two-kernel tail, 1 single-launch tail, 2 low-occupancy)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: fused peer-memory push+merge kernel over NVLink, or NCCL all-gather + merge kernel")
     args = ap.parse_args()
@@ -203,6 +204,7 @@ def main():
     torch.cuda.synchronize()
     index.set_option(N.OPT_TAU_HINT, args.hint)
     index.set_option(N.OPT_PROFILE, 1)
+    index.set_option(N.OPT_TAIL, args.tail)
     searcher = make_sharded_dense(index, exchange=args.exchange, max_nq=w["b"], max_k=w["k"])
     q_dev = synth.dense_queries_torch(w["b"], w["d"], SEED, dev)
     q_pin = torch.empty((w["b"], w["d"]), dtype=torch.float32).pin_memory()
@@ -300,7 +302,7 @@ def main():
             roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                         "frac": achieved_tf / peaks["tf_sustained"],
                         "traffic": read_traffic(args.workload) if world == 1 else None,
-                        "kernel": "dense_fused_kernel<MODE_TOPK>", "kernel_ms": kernel_ms,
+                        "kernel": "dense_fused_pair_kernel<MODE_TOPK>", "kernel_ms": kernel_ms,
                         "peak_source": f"{peaks['source']} MEASURED_PEAKS.json bf16_tflops_sustained",
                         "algorithmic": f"2*B*(N/G)*d = {flops_per_launch:.4g} FLOP per launch; (N/G)*d*2 = {float(n_local) * w['d'] * 2:.4g} B",
                         "traffic_source": "ncu dram__bytes_read+write per launch, profiles/ncu_traffic.json"}
@@ -318,7 +320,8 @@ def main():
                         "h2d_bytes_per_step": w["b"] * w["d"] * 4, "d2h_bytes_per_step": w["b"] * w["k"] * 12},
                 "gpu_launches": int(launches),
                 "search": {"path": int(st.last_path), "overfetch": int(st.last_overfetch), "retried_queries": int(st.retried_queries),
-                           "hint_retries": int(st.hint_retries), "max_abs_tc_err": float(st.max_abs_err)}}
+                           "hint_retries": int(st.hint_retries), "max_abs_tc_err": float(st.max_abs_err),
+                           "tail_ms": st.tail_ms_total / max(1, st.tail_ms_samples)}}
         if not args.no_cpu_baseline and world == 1:
             cpu, _ = cpu_reference_arm(w, 2, 1, args.cpu_rows, None)
             line["cpu_baseline"] = cpu

@@ -14,6 +14,9 @@
  *   vfi_cosine_topk  replaces cosine_similarity + argsort top-k             experiments/retriever/step3_mul.py:255-289,
  *                                                                           experiments/retriever/continuous_retrieval.py:154-167
  *
+ *   vfi_stem_english / vfi_tokenize_ascii  replace Stemmer.Stemmer('english').stemWords and the splitting step of
+ *                    bm25s.tokenize (host-side text routines, no device needed)   src/utils/bm25Retriever.py:14-15,47,67
+ *
  * Conventions
  *   - plain pointers and sizes only; no C++/torch types. `mem` says where caller buffers live.
  *   - the library never returns pointers into its own memory; the caller owns every output buffer.
@@ -104,8 +107,11 @@ enum {
   VFI_OPT_TAU_HINT = 4,      /* 1 (default): estimate a per-query admission threshold from a row sample; 0: off (2: debug, admit nothing) */
   VFI_OPT_NUM_CTAS = 5,      /* 0 = one CTA per SM */
   VFI_OPT_CLUSTER = 6,       /* single-CTA kernel only: CTAs per cluster sharing corpus tiles by TMA multicast: 0/1 off, 2, 4, 8 */
-  VFI_OPT_CTA_PAIR = 7       /* tcgen05 cta_group::2 kernel (two SMs share every corpus tile): 0 auto (on when the batch has an
+  VFI_OPT_CTA_PAIR = 7,      /* tcgen05 cta_group::2 kernel (two SMs share every corpus tile): 0 auto (on when the batch has an
                                 even number of 128-query tiles), 1 off, 2 on */
+  VFI_OPT_TAIL = 8           /* tail after the tensor-core pass for k' <= 256: 0 auto (selection kernel + thread-per-candidate
+                                rescoring kernel, 2-stage ring), 1 the single-launch select+rescore kernel, 2 as 0 with a
+                                3-stage ring */
 };
 int vfi_index_set_option(vfi_index_t* idx, int opt, int64_t value);
 
@@ -121,6 +127,8 @@ typedef struct vfi_search_stats {
   float last_eps;              /* largest certificate epsilon of the last search */
   float max_abs_err;           /* max |tensor-core score - exact score| over rescored candidates */
   int64_t hint_retries;        /* batches redone without the admission hint */
+  double tail_ms_total;        /* summed device time of the selection + rescoring + certificate tail (VFI_OPT_PROFILE=1) */
+  int64_t tail_ms_samples;     /* searches that contributed to tail_ms_total */
 } vfi_search_stats;
 int vfi_index_get_stats(vfi_index_t* idx, vfi_search_stats* out, int reset);
 
@@ -205,6 +213,18 @@ int vfi_fuse_rrf(const int64_t* ids, int64_t nq, int n_paths, int depth, float k
 int vfi_fuse_union(const int64_t* ids, const float* scores, int64_t nq, int n_paths, int depth,
                    int64_t* out_ids, float* out_scores, int32_t* out_path, int32_t* out_count,
                    int mem, int device, void* stream);
+
+/* ---- query/document text (host only; usable without a CUDA device) --------------------------- */
+/* Snowball "english" (Porter2) stemmer, UTF-8.  words: the concatenated bytes of n_words words, word i =
+ * words[offsets[i] .. offsets[i+1]).  out receives the concatenated stems (never longer than the input, so
+ * out_cap >= offsets[n_words] always suffices) and out_offsets [n_words+1] their boundaries.
+ * Replaces Stemmer.Stemmer('english').stemWords(list) (src/utils/bm25Retriever.py:14,47). */
+int vfi_stem_english(const char* words, const int64_t* offsets, int64_t n_words, char* out, int64_t out_cap,
+                     int64_t* out_offsets);
+/* bm25s.tokenize's splitting r"(?u)\b\w\w+\b" for ASCII text: tokens are the maximal runs of [0-9A-Za-z_] of
+ * length >= 2 (byte offsets into text).  *n_tokens = tokens found; at most cap are written.  Text holding a byte
+ * >= 0x80 is refused with VFI_ERR_UNSUPPORTED (the host facade then uses its Unicode-aware pattern). */
+int vfi_tokenize_ascii(const char* text, int64_t len, int64_t* starts, int64_t* lens, int64_t cap, int64_t* n_tokens);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,32 @@ def test_tcgen05_scores_match_fp64_matmul(torch_cuda):
         idx.close()
 
 
+@pytest.mark.parametrize("tail", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("n,d,nq,k,store", [
+    (40000, 1024, 70, 100, "bf16"),      # k' = 128: four full warps of candidates per query
+    (30000, 100, 33, 10, "f32"),         # fp32 rows, d padded to 128, k' = 32
+    (20000, 64, 5, 200, "bf16"),         # k' = 256, one 128-byte row piece
+    (9000, 192, 19, 37, "bf16"),         # k' = 64, row length not a multiple of 256 bytes
+])
+def test_tail_variants_match_oracle(torch_cuda, tail, n, d, nq, k, store):
+    """Every implementation of the selection + canonical rescoring + certificate tail (VFI_OPT_TAIL) is bit-exact."""
+    torch = torch_cuda
+    from oracle import flat_ip
+    from veritasfi_b200 import _native as N
+    from veritasfi_b200.dense import DenseIndex
+    xb, xq = _world(n, d, nq, 11, store == "bf16")
+    idx = DenseIndex(d, store=store)
+    idx.add(xb)
+    idx.set_option(N.OPT_FORCE_PATH, N.PATH_FUSED)
+    idx.set_option(N.OPT_TAIL, tail)
+    ids, scores = idx.search_batch(torch.from_numpy(xq).cuda(), k)
+    ob, oq = _oracle_inputs(xb, xq, store)
+    D0, I0 = flat_ip.search(oq, ob, k)
+    assert (ids.cpu().numpy() == I0).all()
+    assert (scores.cpu().numpy() == D0).all()
+    idx.close()
+
+
 @pytest.mark.parametrize("n,d,nq,k,store,path", [
     (30000, 128, 40, 10, "bf16", 2),
     (100000, 1024, 300, 100, "bf16", 2),     # 3 query tiles -> grouped CTAs share corpus tiles

@@ -11,7 +11,7 @@ from .build import LIB_PATH
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_INTERNAL = range(7)
 MEM_HOST, MEM_DEVICE = 0, 1
 STORE_BF16, STORE_F32 = 0, 1
-OPT_OVERFETCH, OPT_FORCE_PATH, OPT_PROFILE, OPT_TAU_HINT, OPT_NUM_CTAS, OPT_CLUSTER, OPT_CTA_PAIR = 1, 2, 3, 4, 5, 6, 7
+OPT_OVERFETCH, OPT_FORCE_PATH, OPT_PROFILE, OPT_TAU_HINT, OPT_NUM_CTAS, OPT_CLUSTER, OPT_CTA_PAIR, OPT_TAIL = 1, 2, 3, 4, 5, 6, 7, 8
 PATH_AUTO, PATH_EXHAUSTIVE, PATH_FUSED, PATH_GEMV = 0, 1, 2, 3
 MAX_K = 2048
 IPC_HANDLE_BYTES = 64
@@ -32,7 +32,7 @@ class SearchStats(C.Structure):
         ("searches", C.c_int64), ("queries", C.c_int64), ("retried_queries", C.c_int64),
         ("fused_launches", C.c_int64), ("fused_ms_total", C.c_double), ("fused_ms_samples", C.c_int64),
         ("last_path", C.c_int), ("last_overfetch", C.c_int), ("last_eps", C.c_float), ("max_abs_err", C.c_float),
-        ("hint_retries", C.c_int64),
+        ("hint_retries", C.c_int64), ("tail_ms_total", C.c_double), ("tail_ms_samples", C.c_int64),
     ]
 
 
@@ -80,6 +80,8 @@ _SIGNATURES = {
     "vfi_bm25_set_profile": (C.c_int, [_P, C.c_int]),
     "vfi_bm25_get_stats": (C.c_int, [_P, C.POINTER(Bm25Stats), C.c_int]),
     "vfi_fuse_rrf": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
+    "vfi_stem_english": (C.c_int, [C.c_char_p, _P, C.c_int64, _P, C.c_int64, _P]),
+    "vfi_tokenize_ascii": (C.c_int, [C.c_char_p, C.c_int64, _P, _P, C.c_int64, _P]),
     "vfi_fuse_union": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -47,6 +47,17 @@ def _stem(stemmer, words: list[str]) -> list[str]:
     raise TypeError("stemmer must expose stemWords(list) or be callable")
 
 
+def _split(text: str) -> list[str]:
+    """Token strings of the bm25s pattern: the native ASCII splitter (vfi_tokenize_ascii) when the text is ASCII,
+    the Unicode-aware regular expression otherwise (both are host-side and give the same tokens on ASCII text)."""
+    if text.isascii():
+        from .stemmer import tokenize_ascii_native
+        toks = tokenize_ascii_native(text)
+        if toks is not None:
+            return toks
+    return _TOKEN_RE.findall(text)
+
+
 def tokenize(texts, stopwords="english", stemmer=None, lower: bool = True, return_ids: bool = True,
              show_progress: bool = False, **_ignored):
     """bm25s.tokenize: lower-case, regex `\\b\\w\\w+\\b`, stop-word removal, optional stemming of the
@@ -65,7 +76,7 @@ def tokenize(texts, stopwords="english", stemmer=None, lower: bool = True, retur
         if lower:
             text = text.lower()
         doc = []
-        for tok in _TOKEN_RE.findall(text):
+        for tok in _split(text):
             if tok in stop:
                 continue
             if tok not in vocab:

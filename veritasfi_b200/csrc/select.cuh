@@ -8,12 +8,15 @@ namespace vfi {
 
 constexpr uint32_t kSortCap = 4096;  // keys sortable in shared memory by one CTA (32 KB)
 
-struct SelectSmem {
-  uint64_t keys[kSortCap];
+template <uint32_t CAP>
+struct SelectSmemT {
+  static constexpr uint32_t kCap = CAP;   // keys sortable in shared memory (multiple of 256)
+  uint64_t keys[CAP];
   uint32_t hist[256];
   uint32_t ctr;
   uint32_t digit, before, cnt, seen;
 };
+using SelectSmem = SelectSmemT<kSortCap>;
 
 __device__ __forceinline__ uint32_t next_pow2(uint32_t x) {
   uint32_t p = 1;
@@ -55,9 +58,11 @@ __device__ __forceinline__ void hist_find_bin(const uint32_t* hist, uint32_t rem
 // descending at the front and returns that count.  blockDim.x must be 256, n <= kSortCap.
 // Above 1024 keys a full sort is wasteful: the k-th largest of the 256 per-thread maxima is a lower
 // bound of the k-th largest key, so only keys at or above it (about k of them) need sorting.
-__device__ __forceinline__ uint32_t block_topk_smem(SelectSmem* sm, uint32_t n, uint32_t k) {
+template <class SM>
+__device__ __forceinline__ uint32_t block_topk_smem(SM* sm, uint32_t n, uint32_t k) {
   const uint32_t tid = threadIdx.x;
-  constexpr uint32_t kPer = kSortCap / 256;
+  constexpr uint32_t kCap = SM::kCap;
+  constexpr uint32_t kPer = kCap / 256;
   if (n > 1024 && k < n && k <= 256) {
     uint64_t mine[kPer];
     uint64_t mx = 0ull;
@@ -89,10 +94,11 @@ __device__ __forceinline__ uint32_t block_topk_smem(SelectSmem* sm, uint32_t n, 
 // Src: struct with   template<class F> __device__ void for_each(F f) const
 // calling f(key) for the keys assigned to this thread (each key visited by exactly one thread).
 // Leaves the min(total,k) best keys sorted descending in sm->keys[0..); returns that count.
-// Keys must be distinct and != 0.  k <= kSortCap.  All 256 threads of the block must call.
-template <class Src>
-__device__ uint32_t block_topk(const Src& src, uint32_t total, uint32_t k, SelectSmem* sm) {
+// Keys must be distinct and != 0.  k <= SM::kCap.  All 256 threads of the block must call.
+template <class Src, class SM>
+__device__ uint32_t block_topk(const Src& src, uint32_t total, uint32_t k, SM* sm) {
   const uint32_t tid = threadIdx.x;
+  constexpr uint32_t kSortCap = SM::kCap;   // shadows the namespace constant: every bound below is this buffer's
   if (total <= kSortCap) {
     // stage once, select in shared memory
     if (tid == 0) sm->ctr = 0;

@@ -21,6 +21,7 @@
 #include "dense_support.cuh"
 #include "sparse_fuse.cuh"
 #include "peer_exchange.cuh"
+#include "text_host.h"
 
 namespace {
 
@@ -223,12 +224,12 @@ struct vfi_index {
   float* master = nullptr; // [cap_rows][dp] fp32 rows (F32 store only)
   uint32_t* xnorm_bits = nullptr;
   // options
-  int64_t opt_overfetch = 0, opt_force_path = 0, opt_profile = 0, opt_tau_hint = 1, opt_num_ctas = 0, opt_cluster = 0, opt_cta_pair = 0;
+  int64_t opt_overfetch = 0, opt_force_path = 0, opt_profile = 0, opt_tau_hint = 1, opt_num_ctas = 0, opt_cluster = 0, opt_cta_pair = 0, opt_tail = 0;
   // workspace
   DevBuf w_qin, w_qcanon, w_qg, w_eps, w_cand, w_cand_count, w_keys, w_keys_n, w_bound, w_keys2, w_flag,
       w_out_scores, w_out_ids, w_stage, w_dbg, w_sel, w_tau;
   int* h_flag = nullptr;   // pinned: [0] = n_flagged, [1..] = flagged query ids
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   vfi_search_stats stats{};
   uint32_t* d_max_err = nullptr;
   std::mutex mu;
@@ -274,6 +275,8 @@ int vfi_index_create(int d, int store_dtype, int device, vfi_index_t** out) {
     return bail(fail(VFI_ERR_NOMEM, "cudaMallocHost failed"));
   cudaEventCreate(&idx->ev0);
   cudaEventCreate(&idx->ev1);
+  cudaEventCreate(&idx->ev2);
+  cudaEventCreate(&idx->ev3);
   cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kDenseSmemBytes);
   cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kDenseSmemBytes);
   cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_TOPK>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
@@ -282,6 +285,25 @@ int vfi_index_create(int d, int store_dtype, int device, vfi_index_t** out) {
   gemv_set_smem_attr();
   cudaFuncSetAttribute(vfi::select_rescore_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(vfi::TailSmem)));
   cudaFuncSetAttribute(vfi::select_rescore_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(vfi::TailSmem)));
+  {
+    const int rf2 = static_cast<int>(vfi::rescore_finalize_smem(vfi::kRfMaxDp, 256, 2));
+    const int rf3 = static_cast<int>(vfi::rescore_finalize_smem(vfi::kRfMaxDp, 256, 3));
+    cudaFuncSetAttribute(vfi::rescore_finalize_kernel<uint16_t, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rf2);
+    cudaFuncSetAttribute(vfi::rescore_finalize_kernel<float, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rf2);
+    cudaFuncSetAttribute(vfi::rescore_finalize_kernel<uint16_t, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rf2);
+    cudaFuncSetAttribute(vfi::rescore_finalize_kernel<float, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rf2);
+#define VFI_RFB_ATTR(P, S)                                                                                                      \
+  cudaFuncSetAttribute(vfi::rescore_finalize_bulk_kernel<uint16_t, P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                       static_cast<int>(vfi::rescore_bulk_smem<P>(vfi::kRfMaxDp, 256, S)));                                      \
+  cudaFuncSetAttribute(vfi::rescore_finalize_bulk_kernel<float, P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                       static_cast<int>(vfi::rescore_bulk_smem<P>(vfi::kRfMaxDp, 256, S)))
+    VFI_RFB_ATTR(128, 3);
+    VFI_RFB_ATTR(128, 2);
+    VFI_RFB_ATTR(256, 2);
+#undef VFI_RFB_ATTR
+    cudaFuncSetAttribute(vfi::rescore_finalize_kernel<uint16_t, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rf3);
+    cudaFuncSetAttribute(vfi::rescore_finalize_kernel<float, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rf3);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return bail(fail(VFI_ERR_CUDA, std::string("kernel attribute setup: ") + cudaGetErrorString(e)));
   *out = idx;
@@ -298,6 +320,8 @@ int vfi_index_destroy(vfi_index_t* idx) {
   if (idx->h_flag) cudaFreeHost(idx->h_flag);
   if (idx->ev0) cudaEventDestroy(idx->ev0);
   if (idx->ev1) cudaEventDestroy(idx->ev1);
+  if (idx->ev2) cudaEventDestroy(idx->ev2);
+  if (idx->ev3) cudaEventDestroy(idx->ev3);
   for (DevBuf* b : {&idx->w_qin, &idx->w_qcanon, &idx->w_qg, &idx->w_eps, &idx->w_cand, &idx->w_cand_count, &idx->w_keys,
                     &idx->w_keys_n, &idx->w_bound, &idx->w_keys2, &idx->w_flag, &idx->w_out_scores, &idx->w_out_ids,
                     &idx->w_stage, &idx->w_dbg, &idx->w_sel, &idx->w_tau})
@@ -415,6 +439,10 @@ int vfi_index_set_option(vfi_index_t* idx, int opt, int64_t value) {
     case VFI_OPT_CTA_PAIR:
       if (value < 0 || value > 2) return fail(VFI_ERR_INVALID, "VFI_OPT_CTA_PAIR: 0 auto, 1 off, 2 on");
       idx->opt_cta_pair = value;
+      break;
+    case VFI_OPT_TAIL:
+      if (value < 0 || value > 6) return fail(VFI_ERR_INVALID, "VFI_OPT_TAIL: 0 auto, 1 single-launch tail, 2 three-stage rescoring ring");
+      idx->opt_tail = value;
       break;
     case VFI_OPT_CLUSTER:
       if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(VFI_ERR_INVALID, "cluster must be 1, 2, 4 or 8");
@@ -708,8 +736,53 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
   VFI_TRY(idx->w_flag.ensure(static_cast<size_t>(kMaxQueriesPerLaunch + 1) * 4));
   int* d_flag = idx->w_flag.as<int>();
   VFI_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
-  if (keep <= 256) {
-    // fused tail: union of the group buffers + k' selection + canonical rescoring + certificate in one launch
+  const bool tail_prof = idx->opt_profile != 0;
+  if (tail_prof) cudaEventRecord(idx->ev2, st);
+  if (keep <= 256 && idx->dp <= vfi::kRfMaxDp && idx->opt_tail != 1) {
+    // K1c: per-query union of the group buffers -> k' best by tensor-core score; then K2: one thread per candidate
+    // rescoring + final order + certificate
+    VFI_TRY(idx->w_keys.ensure(static_cast<size_t>(nq) * keep * 8));
+    VFI_TRY(idx->w_keys_n.ensure(static_cast<size_t>(nq) * 4));
+    VFI_TRY(idx->w_bound.ensure(static_cast<size_t>(nq) * 4));
+    vfi::cand_reduce_kernel<vfi::CandSmem><<<nq, 256, sizeof(vfi::CandSmem), st>>>(idx->w_cand.as<uint64_t>(), idx->w_cand_count.as<uint32_t>(),
+                                                                     n_groups, nq_pad, cap, keep, tau, idx->w_keys.as<uint64_t>(),
+                                                                     idx->w_keys_n.as<uint32_t>(), idx->w_bound.as<float>());
+    LAUNCHED();
+    VFI_CUDA(cudaGetLastError());
+    const int threads = static_cast<int>(round_up(keep, 32));
+    const int stages = idx->opt_tail == 2 ? 3 : 2;
+    const size_t smem = vfi::rescore_finalize_smem(static_cast<int>(idx->dp), threads, stages);
+#define VFI_RF_LAUNCH(T, STAGES, PF, ROWS, PITCH)                                                                        \
+  vfi::rescore_finalize_kernel<T, STAGES, PF><<<nq, threads, smem, st>>>(                                                \
+      idx->w_keys.as<uint64_t>(), idx->w_keys_n.as<uint32_t>(), idx->w_bound.as<float>(), keep, ROWS, PITCH,             \
+      static_cast<int>(idx->dp), idx->w_qcanon.as<float>(), k, idx->id_offset, idx->w_eps.as<float>(), out_scores, out_ids, \
+      d_flag + 1, d_flag, idx->d_max_err)
+#define VFI_RFB_LAUNCH(T, P, S, ROWS, PITCH)                                                                             \
+  vfi::rescore_finalize_bulk_kernel<T, P, S><<<nq, threads, vfi::rescore_bulk_smem<P>(static_cast<int>(idx->dp), threads, S), st>>>( \
+      idx->w_keys.as<uint64_t>(), idx->w_keys_n.as<uint32_t>(), idx->w_bound.as<float>(), keep, ROWS, PITCH,             \
+      static_cast<int>(idx->dp), idx->w_qcanon.as<float>(), k, idx->id_offset, idx->w_eps.as<float>(), out_scores, out_ids, \
+      d_flag + 1, d_flag, idx->d_max_err)
+    if (idx->opt_tail >= 4) {
+      const bool f32 = idx->store == VFI_STORE_F32;
+      if (idx->opt_tail == 4) { if (f32) VFI_RFB_LAUNCH(float, 128, 3, idx->master, idx->dp); else VFI_RFB_LAUNCH(uint16_t, 128, 3, idx->g, idx->kp); }
+      else if (idx->opt_tail == 5) { if (f32) VFI_RFB_LAUNCH(float, 256, 2, idx->master, idx->dp); else VFI_RFB_LAUNCH(uint16_t, 256, 2, idx->g, idx->kp); }
+      else { if (f32) VFI_RFB_LAUNCH(float, 128, 2, idx->master, idx->dp); else VFI_RFB_LAUNCH(uint16_t, 128, 2, idx->g, idx->kp); }
+    } else
+    if (idx->store == VFI_STORE_F32) {
+      if (stages == 3) VFI_RF_LAUNCH(float, 3, true, idx->master, idx->dp);
+      else if (idx->opt_tail == 3) VFI_RF_LAUNCH(float, 2, false, idx->master, idx->dp);
+      else VFI_RF_LAUNCH(float, 2, true, idx->master, idx->dp);
+    } else {
+      if (stages == 3) VFI_RF_LAUNCH(uint16_t, 3, true, idx->g, idx->kp);
+      else if (idx->opt_tail == 3) VFI_RF_LAUNCH(uint16_t, 2, false, idx->g, idx->kp);
+      else VFI_RF_LAUNCH(uint16_t, 2, true, idx->g, idx->kp);
+    }
+#undef VFI_RF_LAUNCH
+#undef VFI_RFB_LAUNCH
+    LAUNCHED();
+    VFI_CUDA(cudaGetLastError());
+  } else if (keep <= 256) {
+    // single-launch tail: union of the group buffers + k' selection + canonical rescoring + certificate
     if (idx->store == VFI_STORE_F32)
       vfi::select_rescore_kernel<float><<<nq, 256, sizeof(vfi::TailSmem), st>>>(
           idx->w_cand.as<uint64_t>(), idx->w_cand_count.as<uint32_t>(), n_groups, nq_pad, cap, keep, tau, idx->master, idx->dp,
@@ -727,7 +800,7 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
     VFI_TRY(idx->w_keys.ensure(static_cast<size_t>(nq) * keep * 8));
     VFI_TRY(idx->w_keys_n.ensure(static_cast<size_t>(nq) * 4));
     VFI_TRY(idx->w_bound.ensure(static_cast<size_t>(nq) * 4));
-    vfi::cand_reduce_kernel<<<nq, 256, sizeof(vfi::SelectSmem), st>>>(idx->w_cand.as<uint64_t>(), idx->w_cand_count.as<uint32_t>(),
+    vfi::cand_reduce_kernel<vfi::SelectSmem><<<nq, 256, sizeof(vfi::SelectSmem), st>>>(idx->w_cand.as<uint64_t>(), idx->w_cand_count.as<uint32_t>(),
                                                                      n_groups, nq_pad, cap, keep, tau, idx->w_keys.as<uint64_t>(),
                                                                      idx->w_keys_n.as<uint32_t>(), idx->w_bound.as<float>());
     LAUNCHED();
@@ -753,10 +826,17 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
     LAUNCHED();
     VFI_CUDA(cudaGetLastError());
   }
+  if (tail_prof) cudaEventRecord(idx->ev3, st);
   VFI_CUDA(cudaMemcpyAsync(idx->h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
   VFI_CUDA(cudaStreamSynchronize(st));
   if (idx->opt_profile) {
     float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, idx->ev2, idx->ev3) == cudaSuccess) {
+      idx->stats.tail_ms_total += ms;
+      idx->stats.tail_ms_samples++;
+    } else {
+      cudaGetLastError();
+    }
     if (cudaEventElapsedTime(&ms, idx->ev0, idx->ev1) == cudaSuccess) {
       idx->stats.fused_ms_total += ms;
       idx->stats.fused_ms_samples++;
@@ -1463,7 +1543,7 @@ int vfi_bm25_search(vfi_bm25_t* b, const int32_t* q_tokens, const int64_t* q_ind
   if (b->profile) cudaEventRecord(b->ev1, st);
   VFI_CUDA(cudaGetLastError());
   b->stats.launches++;
-  vfi::cand_reduce_kernel<<<static_cast<unsigned>(nq), 256, sizeof(vfi::SelectSmem), st>>>(
+  vfi::cand_reduce_kernel<vfi::SelectSmem><<<static_cast<unsigned>(nq), 256, sizeof(vfi::SelectSmem), st>>>(
       b->w_cand.as<uint64_t>(), b->w_cand_count.as<uint32_t>(), static_cast<int>(n_seg), static_cast<int>(nq), keep, keep, nullptr,
       b->w_keys.as<uint64_t>(), b->w_keys_n.as<uint32_t>(), b->w_bound.as<float>());
   LAUNCHED();
@@ -1604,4 +1684,36 @@ extern "C" int vfi_bm25_rank_all(vfi_bm25_t* b, const int32_t* q_tokens, int64_t
   VFI_CUDA(cudaMemcpyAsync(out_ids, ids.p, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, st));
   VFI_CUDA(cudaStreamSynchronize(st));
   return VFI_OK;
+}
+
+extern "C" {
+// ---- host-side text routines (no device involved) -------------------------------------------------
+int vfi_stem_english(const char* words, const int64_t* offsets, int64_t n_words, char* out, int64_t out_cap,
+                     int64_t* out_offsets) {
+  if (n_words < 0 || !offsets || !out_offsets || (n_words > 0 && (!words || !out)))
+    return fail(VFI_ERR_INVALID, "bad argument to vfi_stem_english");
+  vfi_text::EnglishStemmer st;
+  int64_t pos = 0;
+  out_offsets[0] = 0;
+  for (int64_t i = 0; i < n_words; ++i) {
+    const int64_t a = offsets[i], b = offsets[i + 1];
+    if (a < 0 || b < a) return fail(VFI_ERR_INVALID, "vfi_stem_english: offsets must be non-decreasing");
+    const std::string& r = st.stem(words + a, static_cast<size_t>(b - a));
+    if (pos + static_cast<int64_t>(r.size()) > out_cap) return fail(VFI_ERR_INVALID, "vfi_stem_english: out_cap too small");
+    std::memcpy(out + pos, r.data(), r.size());
+    pos += static_cast<int64_t>(r.size());
+    out_offsets[i + 1] = pos;
+  }
+  return VFI_OK;
+}
+
+int vfi_tokenize_ascii(const char* text, int64_t len, int64_t* starts, int64_t* lens, int64_t cap, int64_t* n_tokens) {
+  if (len < 0 || cap < 0 || !n_tokens || (len > 0 && !text) || (cap > 0 && (!starts || !lens)))
+    return fail(VFI_ERR_INVALID, "bad argument to vfi_tokenize_ascii");
+  const int64_t n = vfi_text::tokenize_ascii(text, len, starts, lens, cap);
+  if (n < 0) return fail(VFI_ERR_UNSUPPORTED, "vfi_tokenize_ascii: non-ASCII text");
+  *n_tokens = n;
+  return VFI_OK;
+}
+
 }

@@ -13,7 +13,7 @@ import sys
 import types
 
 from . import bm25_compat, faiss_compat
-from .retrievers import _IdentityStemmer
+from . import stemmer as native_stemmer
 
 
 def _module(name: str, **attrs) -> types.ModuleType:
@@ -36,7 +36,8 @@ def install(override_stemmer: bool = False) -> None:
         except Exception:
             have_real = False
     if not have_real:
-        sys.modules["Stemmer"] = _module("Stemmer", Stemmer=_IdentityStemmer, _vfi_shim=True)
+        sys.modules["Stemmer"] = _module("Stemmer", Stemmer=native_stemmer.Stemmer, algorithms=native_stemmer.algorithms,
+                                         _vfi_shim=True)
 
 
 def uninstall() -> None:

@@ -30,7 +30,7 @@ MAX_EXPANDED = 4            # ensembleRetriever.py:89
 
 
 class _IdentityStemmer:
-    """Stand-in when PyStemmer is not installed: tokens are left unstemmed."""
+    """Leaves tokens unstemmed (used by the golden fixtures, which were generated without a stemmer)."""
 
     def __init__(self, lang: str = "english"):
         self.lang = lang
@@ -40,13 +40,16 @@ class _IdentityStemmer:
 
 
 def make_stemmer(lang: str = "english"):
+    """`Stemmer.Stemmer(lang)` of bm25Retriever.py:14,47.  PyStemmer when the deployment has it, else the native
+    Snowball-English routine of this package (csrc/text_host.h behind vfi_stem_english)."""
     try:
         import Stemmer  # PyStemmer, if the deployment has it
         if hasattr(Stemmer, "Stemmer") and not getattr(Stemmer, "_vfi_shim", False):
             return Stemmer.Stemmer(lang)
     except Exception:
         pass
-    return _IdentityStemmer(lang)
+    from .stemmer import Stemmer as NativeStemmer
+    return NativeStemmer(lang)
 
 
 class FaissRetriever:
