@@ -153,7 +153,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=250_000, help="rows of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hint", type=int, default=1)
-    ap.add_argument("--tail", type=int, default=0, help="VFI_OPT_TAIL (0 default two-kernel tail, 1 single-launch tail, 2 low-occupancy)")
+    ap.add_argument("--tail", type=int, default=0, help="VFI_OPT_TAIL (0 default: selection kernel + bulk-copy rescoring kernel, 1 single-launch tail, 2/3 variants)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: fused peer-memory push+merge kernel over NVLink, or NCCL all-gather + merge kernel")
     args = ap.parse_args()

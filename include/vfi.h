@@ -109,9 +109,9 @@ enum {
   VFI_OPT_CLUSTER = 6,       /* single-CTA kernel only: CTAs per cluster sharing corpus tiles by TMA multicast: 0/1 off, 2, 4, 8 */
   VFI_OPT_CTA_PAIR = 7,      /* tcgen05 cta_group::2 kernel (two SMs share every corpus tile): 0 auto (on when the batch has an
                                 even number of 128-query tiles), 1 off, 2 on */
-  VFI_OPT_TAIL = 8           /* tail after the tensor-core pass for k' <= 256: 0 auto (selection kernel + thread-per-candidate
-                                rescoring kernel, 2-stage ring), 1 the single-launch select+rescore kernel, 2 as 0 with a
-                                3-stage ring */
+  VFI_OPT_TAIL = 8           /* tail after the tensor-core pass for k' <= 256: 0 auto (selection kernel, then a thread-per-candidate
+                                rescoring kernel fed by 256-byte bulk copies), 1 the single-launch select+rescore kernel,
+                                2 as 0 with 128-byte pieces (1024 queries in one wave), 3 as 0 with a two-stage ring */
 };
 int vfi_index_set_option(vfi_index_t* idx, int opt, int64_t value);
 

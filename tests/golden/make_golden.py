@@ -3,7 +3,8 @@
 
 The reference's third-party dependencies are absent from this image (faiss, bm25s, PyStemmer, langchain_*),
 so they are replaced by shims: `faiss` and the scoring half of `bm25s` are backed by the CPU ORACLE (oracle/),
-tokenisation by the host tokenizer of veritasfi_b200.bm25_compat, PyStemmer by an identity stemmer.  What the
+tokenisation by the host tokenizer of veritasfi_b200.bm25_compat, PyStemmer by the oracle's Snowball-English
+restatement (oracle/porter2.py).  What the
 fixture pins is therefore the reference's own orchestration — depth-2048 dense search, shared seen_ids
 de-duplication, bundle gathering, prev/next expansion at 0.72/0.66, title-summary mapping, BM25 k = N then
 slice — on top of the canonical arithmetic.  Run in the build container only (needs /root/reference):
@@ -26,7 +27,7 @@ import fixture_world as fw  # noqa: E402
 REFERENCE = "/root/reference"
 
 
-from oracle_doubles import IdentityStemmer, install_reference_shims, write_bm25_dir  # noqa: E402
+from oracle_doubles import install_reference_shims, write_bm25_dir  # noqa: E402
 
 
 def main():

@@ -6,7 +6,7 @@ import types
 
 import numpy as np
 
-from oracle import bm25 as obm, flat_ip
+from oracle import bm25 as obm, flat_ip, porter2
 from veritasfi_b200 import bm25_compat
 
 
@@ -54,6 +54,19 @@ class IdentityStemmer:
         return list(ws)
 
 
+class OracleStemmer:
+    """PyStemmer's Stemmer.Stemmer('english') backed by the oracle restatement of Snowball English (oracle/porter2.py)."""
+
+    def __init__(self, lang="english"):
+        assert lang == "english"
+
+    def stemWord(self, w):
+        return porter2.stem(w)
+
+    def stemWords(self, ws):
+        return porter2.stem_words(ws)
+
+
 def install_reference_shims():
     def mod(name, **kw):
         m = types.ModuleType(name)
@@ -62,7 +75,7 @@ def install_reference_shims():
         return m
     mod("faiss", IndexFlatIP=OracleIndexFlatIP, normalize_L2=oracle_normalize_L2)
     mod("bm25s", BM25=OracleBM25, tokenize=bm25_compat.tokenize)
-    mod("Stemmer", Stemmer=IdentityStemmer)
+    mod("Stemmer", Stemmer=OracleStemmer)
     mod("langchain_huggingface", HuggingFaceEmbeddings=object)
     mod("langchain_community")
     mod("langchain_community.vectorstores", FAISS=object)
@@ -73,7 +86,7 @@ def install_reference_shims():
 
 def write_bm25_dir(world, path):
     eng = bm25_compat.BM25()
-    eng.index(bm25_compat.tokenize(world["texts"], stopwords="english", stemmer=IdentityStemmer()))
+    eng.index(bm25_compat.tokenize(world["texts"], stopwords="english", stemmer=OracleStemmer()))
     eng.save(path, corpus=[m["doc_id"] for m in world["metas"]])
 
 

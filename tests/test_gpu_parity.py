@@ -47,7 +47,7 @@ def test_tcgen05_scores_match_fp64_matmul(torch_cuda):
         idx.close()
 
 
-@pytest.mark.parametrize("tail", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("tail", [0, 1, 2, 3])
 @pytest.mark.parametrize("n,d,nq,k,store", [
     (40000, 1024, 70, 100, "bf16"),      # k' = 128: four full warps of candidates per query
     (30000, 100, 33, 10, "f32"),         # fp32 rows, d padded to 128, k' = 32

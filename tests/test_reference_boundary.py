@@ -58,7 +58,7 @@ def test_mirror_with_oracle_doubles_reproduces_the_reference(tmp_path, monkeypat
     monkeypatch.setattr(retrievers.faiss_compat, "IndexFlatIP", od.OracleIndexFlatIP)
     monkeypatch.setattr(retrievers.faiss_compat, "normalize_L2", od.oracle_normalize_L2)
     monkeypatch.setattr(retrievers.bm25_compat, "BM25", od.OracleBM25)
-    monkeypatch.setattr(retrievers, "make_stemmer", lambda lang="english": od.IdentityStemmer())
+    monkeypatch.setattr(retrievers, "make_stemmer", lambda lang="english": od.OracleStemmer())
     _assert_equal_to_golden(_run(retrievers.EnsembleRetriever, str(tmp_path), world))
 
 

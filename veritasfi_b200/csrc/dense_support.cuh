@@ -553,162 +553,23 @@ __global__ void __launch_bounds__(256, 3) select_rescore_kernel(
 
 // ------------------------------------------------------------------------------------------
 // K2 fused (k' <= 256): canonical rescoring + final order + certificate.  One CTA per query, ONE THREAD PER
-// CANDIDATE, every warp busy.  Measured on B200 (tools/ubench/fp64_rates.cu): DFMA issues at 64 lanes/clk/SM with a
-// 12-cycle dependent latency and F2F.F64.F32 at 16 lanes/clk/SM, so the sequential fp64 chain wants >= 512 resident
-// threads per SM; the floor of the kernel is the HBM read of the candidate rows (nq * k' * d * sizeof(RowT) bytes).
-// Rows move in 64-byte chunks by cp.async (4 lanes per row, no registers), through a per-warp ring of STAGES tiles in
-// shared memory (XOR-swizzled 64-byte rows: conflict-free 128-bit access for the copies and for the owner lane's walk).  The query
-// is widened to fp64 once per CTA.  With STAGES = 2 seven 128-thread CTAs fit an SM, so 1024 queries are one wave.
+// CANDIDATE, every warp busy.  Measured on B200 (tools/ubench/fp64_rates.cu, gather_rows.cu; profiles/r1_tail.md):
+//   * DFMA issues at 64 lanes/clk/SM with a 12-cycle dependent latency, F2F.F64.F32 at 16 lanes/clk/SM: the sequential
+//     fp64 chain needs >= 16 resident warps per SM to reach the conversion rate;
+//   * a gather of random 2 KB rows runs at 2.2 TB/s in 64-byte pieces, 3.8 TB/s in 128-byte pieces and 5.6 TB/s in
+//     256-byte pieces, however the pieces are requested (LDG, cp.async with or without L2::256B, bulk copies).
+// So every lane fetches PIECE = 256 contiguous bytes of ITS OWN row per step with one 1D bulk copy (cp.async.bulk,
+// completion on a per-warp mbarrier) straight into its own padded shared-memory row: no LSU load instruction, no register
+// staging, no transposition.  One stage per warp; the other resident warps (20 per SM) hide the copy.  The query is
+// widened to fp64 once per CTA.  Floor: the HBM read of the candidate rows, nq * k' * d * sizeof(RowT) bytes.
 // ------------------------------------------------------------------------------------------
-constexpr int kRfChunkBytes = 64;
-constexpr int kRfPitch = 16;            // words per staged row chunk; the four 16-byte pieces of row r sit at piece ^ ((r >> 1) & 3)
-constexpr int kRfPrefetchBytes = 256;
 constexpr int kRfMaxDp = 4096;          // query held as fp64 in shared memory (32 KB at the limit)
-__host__ __device__ inline size_t rescore_finalize_smem(int dp, int threads, int stages) {
-  return static_cast<size_t>(dp) * 8 + 256 * 8 + static_cast<size_t>(threads / 32) * stages * 32 * kRfPitch * 4;
-}
-
-template <typename RowT, int STAGES, bool PREFETCH>
-__global__ void __launch_bounds__(256, 3) rescore_finalize_kernel(
-    const uint64_t* __restrict__ cand_keys, const uint32_t* __restrict__ n_cand, const float* __restrict__ bound,
-    int keep, const RowT* __restrict__ rows, int64_t row_pitch, int dp, const float* __restrict__ qcanon, int k,
-    int64_t id_offset, const float* __restrict__ eps, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
-    int* __restrict__ flagged, int* __restrict__ n_flagged, uint32_t* __restrict__ max_err_bits) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  double* qd = reinterpret_cast<double*>(smem_raw);
-  uint64_t* skeys = reinterpret_cast<uint64_t*>(qd + dp);
-  uint32_t* tiles = reinterpret_cast<uint32_t*>(skeys + 256);
-  __shared__ uint32_t s_err;
-  const int q = blockIdx.x;
-  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t n = min(n_cand[q], static_cast<uint32_t>(keep));
-  const bool valid = tid < n;
-  uint32_t id = 0;
-  float tc = 0.f;
-  if (valid) {
-    const uint64_t ck = cand_keys[static_cast<int64_t>(q) * keep + tid];
-    id = key_id(ck);
-    tc = key_score(ck);
-  }
-  if (tid == 0) s_err = 0;
-  // this lane copies the 16-byte piece (lane & 3) of the chunk of rows (lane >> 2) + 8*it, it = 0..3
-  const uint32_t piece = lane & 3, rsub = lane >> 2;
-  const int64_t row_bytes = row_pitch * static_cast<int64_t>(sizeof(RowT));
-  const uint8_t* src[4];
-  uint32_t vbytes[4];
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int r = it * 8 + static_cast<int>(rsub);
-    const uint32_t rid = __shfl_sync(0xFFFFFFFFu, id, r);
-    const bool rv = __shfl_sync(0xFFFFFFFFu, valid ? 1 : 0, r) != 0;
-    src[it] = reinterpret_cast<const uint8_t*>(rows) + (rv ? static_cast<int64_t>(rid) * row_bytes : 0) + piece * 16;
-    vbytes[it] = rv ? 16u : 0u;
-  }
-  uint32_t* ring = tiles + warp * STAGES * 32 * kRfPitch;
-  const int n_chunks = dp * static_cast<int>(sizeof(RowT)) / kRfChunkBytes;   // dp is a multiple of 64
-  // L2 prefetch of this lane's own row, kRfPrefetchBytes at a time and one block ahead of the 64-byte copies: DRAM then
-  // serves each row in a few long bursts (open-page hits) instead of 32 isolated 64-byte reads
-  const uint8_t* my_row = reinterpret_cast<const uint8_t*>(rows) + static_cast<int64_t>(id) * row_bytes;
-  const int row_len = dp * static_cast<int>(sizeof(RowT));
-  auto prefetch_block = [&](int blk) {
-    const int off = blk * kRfPrefetchBytes;
-    if (valid && off < row_len) ptx::prefetch_l2_bulk(my_row + off, static_cast<uint32_t>(min(kRfPrefetchBytes, row_len - off)));
-  };
-  if (PREFETCH) { prefetch_block(0); prefetch_block(1); }
-  auto issue = [&](int c) {
-    if (c < n_chunks) {
-      uint32_t* t = ring + (c % STAGES) * 32 * kRfPitch;
-#pragma unroll
-      for (int it = 0; it < 4; ++it)
-        ptx::cp_async_16(t + (it * 8 + rsub) * kRfPitch + ((piece ^ ((rsub >> 1) & 3)) * 4), src[it] + static_cast<int64_t>(c) * kRfChunkBytes, vbytes[it]);
-    }
-    ptx::cp_async_commit();
-  };
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) issue(s);
-  const float* qv = qcanon + static_cast<int64_t>(q) * dp;
-  for (int e = tid; e < dp; e += blockDim.x) qd[e] = static_cast<double>(qv[e]);
-  __syncthreads();
-  constexpr int kChunkElems = kRfChunkBytes / static_cast<int>(sizeof(RowT));
-  const uint32_t sw = (lane >> 1) & 3;
-  double acc = 0.0;
-  constexpr int kChunksPerBlock = kRfPrefetchBytes / kRfChunkBytes;
-  for (int c = 0; c < n_chunks; ++c) {
-    if (PREFETCH && (c % kChunksPerBlock) == 0) prefetch_block(c / kChunksPerBlock + 2);
-    issue(c + STAGES - 1);                 // targets the stage consumed in iteration c-1
-    ptx::cp_async_wait<STAGES - 1>();      // this lane's copies of chunk c have landed
-    __syncwarp();                          // ... and so have the other lanes'
-    const uint4* mine = reinterpret_cast<const uint4*>(ring + (c % STAGES) * 32 * kRfPitch + lane * kRfPitch);
-    const double2* qq = reinterpret_cast<const double2*>(qd + c * kChunkElems);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint4 u = mine[i ^ sw];
-      if (sizeof(RowT) == 2) {
-        const double2 q0 = qq[4 * i], q1 = qq[4 * i + 1], q2 = qq[4 * i + 2], q3 = qq[4 * i + 3];
-        const double x0 = static_cast<double>(__uint_as_float(u.x << 16));
-        const double x1 = static_cast<double>(__uint_as_float(u.x & 0xFFFF0000u));
-        const double x2 = static_cast<double>(__uint_as_float(u.y << 16));
-        const double x3 = static_cast<double>(__uint_as_float(u.y & 0xFFFF0000u));
-        const double x4 = static_cast<double>(__uint_as_float(u.z << 16));
-        const double x5 = static_cast<double>(__uint_as_float(u.z & 0xFFFF0000u));
-        const double x6 = static_cast<double>(__uint_as_float(u.w << 16));
-        const double x7 = static_cast<double>(__uint_as_float(u.w & 0xFFFF0000u));
-        acc = fma(q0.x, x0, acc); acc = fma(q0.y, x1, acc);
-        acc = fma(q1.x, x2, acc); acc = fma(q1.y, x3, acc);
-        acc = fma(q2.x, x4, acc); acc = fma(q2.y, x5, acc);
-        acc = fma(q3.x, x6, acc); acc = fma(q3.y, x7, acc);
-      } else {
-        const double2 q0 = qq[2 * i], q1 = qq[2 * i + 1];
-        acc = fma(q0.x, static_cast<double>(__uint_as_float(u.x)), acc);
-        acc = fma(q0.y, static_cast<double>(__uint_as_float(u.y)), acc);
-        acc = fma(q1.x, static_cast<double>(__uint_as_float(u.z)), acc);
-        acc = fma(q1.y, static_cast<double>(__uint_as_float(u.w)), acc);
-      }
-    }
-    __syncwarp();                          // the stage may be refilled by the next iteration's issue
-  }
-  ptx::cp_async_wait<0>();
-  const float s = static_cast<float>(acc);
-  // final order of the n rescored candidates
-  const uint32_t np = max(next_pow2(n), 2u);
-  for (uint32_t i = tid; i < np; i += blockDim.x) skeys[i] = 0ull;
-  __syncthreads();
-  if (valid) skeys[tid] = make_key(s, id);
-  if (max_err_bits != nullptr) {
-    uint32_t e = valid ? __float_as_uint(fabsf(s - tc)) : 0u;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xFFFFFFFFu, e, o));
-    if (lane == 0 && e != 0u) atomicMax(&s_err, e);
-  }
-  block_bitonic_desc(skeys, np);
-  if (max_err_bits != nullptr && tid == 0 && s_err != 0u) atomicMax(max_err_bits, s_err);
-  const float b = bound[q];
-  bool ok = true;
-  if (b != -INFINITY) {
-    if (n < static_cast<uint32_t>(k)) ok = false;
-    else ok = key_score(skeys[k - 1]) > b + eps[q];
-  }
-  if (ok) {
-    for (int i = tid; i < k; i += blockDim.x) {
-      const bool has = static_cast<uint32_t>(i) < n;
-      const uint64_t key = has ? skeys[i] : 0ull;
-      out_scores[static_cast<int64_t>(q) * k + i] = has ? key_score(key) : -3.402823466e+38f;
-      out_ids[static_cast<int64_t>(q) * k + i] = has ? static_cast<int64_t>(key_id(key)) + id_offset : -1;
-    }
-  } else if (tid == 0) {
-    flagged[atomicAdd(n_flagged, 1)] = q;
-  }
-}
-
-// K2 fused, TMA variant: every lane fetches PIECE contiguous bytes of ITS OWN row per step with one 1D bulk copy
-// (cp.async.bulk, completion on a per-warp, per-stage mbarrier) straight into its own padded shared-memory row, so no
-// LSU load instruction, no register staging and no transposition is involved, and DRAM sees PIECE-byte bursts.
 template <int PIECE>
 __host__ __device__ inline size_t rescore_bulk_smem(int dp, int threads, int stages) {
   return static_cast<size_t>(dp) * 8 + 256 * 8 + 8 * 4 * 8 + static_cast<size_t>(threads / 32) * stages * 32 * (PIECE + 16);
 }
 template <typename RowT, int PIECE, int STAGES>
-__global__ void __launch_bounds__(256) rescore_finalize_bulk_kernel(
+__global__ void __launch_bounds__(256) rescore_finalize_kernel(
     const uint64_t* __restrict__ cand_keys, const uint32_t* __restrict__ n_cand, const float* __restrict__ bound,
     int keep, const RowT* __restrict__ rows, int64_t row_pitch, int dp, const float* __restrict__ qcanon, int k,
     int64_t id_offset, const float* __restrict__ eps, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,

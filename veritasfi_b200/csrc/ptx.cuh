@@ -282,11 +282,6 @@ __device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
   return r;
 }
 
-// 16-byte asynchronous copy global -> shared (LDGSTS, bypasses L1 and registers); src_bytes = 0 zero-fills
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, uint32_t src_bytes) {
-  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
-}
 // 1D bulk copy (TMA) of `bytes` (multiple of 16, both addresses 16-byte aligned) global -> this CTA's shared memory,
 // completion signalled as transaction bytes on an mbarrier
 __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -294,13 +289,6 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// bulk prefetch of `bytes` (multiple of 16) contiguous global bytes into L2: one request, so DRAM sees the whole span at once
-__device__ __forceinline__ void prefetch_l2_bulk(const void* gmem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 }  // namespace ptx
 }  // namespace vfi

@@ -285,25 +285,15 @@ int vfi_index_create(int d, int store_dtype, int device, vfi_index_t** out) {
   gemv_set_smem_attr();
   cudaFuncSetAttribute(vfi::select_rescore_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(vfi::TailSmem)));
   cudaFuncSetAttribute(vfi::select_rescore_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(vfi::TailSmem)));
-  {
-    const int rf2 = static_cast<int>(vfi::rescore_finalize_smem(vfi::kRfMaxDp, 256, 2));
-    const int rf3 = static_cast<int>(vfi::rescore_finalize_smem(vfi::kRfMaxDp, 256, 3));
-    cudaFuncSetAttribute(vfi::rescore_finalize_kernel<uint16_t, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rf2);
-    cudaFuncSetAttribute(vfi::rescore_finalize_kernel<float, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rf2);
-    cudaFuncSetAttribute(vfi::rescore_finalize_kernel<uint16_t, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rf2);
-    cudaFuncSetAttribute(vfi::rescore_finalize_kernel<float, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rf2);
-#define VFI_RFB_ATTR(P, S)                                                                                                      \
-  cudaFuncSetAttribute(vfi::rescore_finalize_bulk_kernel<uint16_t, P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                       static_cast<int>(vfi::rescore_bulk_smem<P>(vfi::kRfMaxDp, 256, S)));                                      \
-  cudaFuncSetAttribute(vfi::rescore_finalize_bulk_kernel<float, P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+#define VFI_RF_ATTR(P, S)                                                                                                  \
+  cudaFuncSetAttribute(vfi::rescore_finalize_kernel<uint16_t, P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                       static_cast<int>(vfi::rescore_bulk_smem<P>(vfi::kRfMaxDp, 256, S)));                                 \
+  cudaFuncSetAttribute(vfi::rescore_finalize_kernel<float, P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
                        static_cast<int>(vfi::rescore_bulk_smem<P>(vfi::kRfMaxDp, 256, S)))
-    VFI_RFB_ATTR(128, 3);
-    VFI_RFB_ATTR(128, 2);
-    VFI_RFB_ATTR(256, 2);
-#undef VFI_RFB_ATTR
-    cudaFuncSetAttribute(vfi::rescore_finalize_kernel<uint16_t, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rf3);
-    cudaFuncSetAttribute(vfi::rescore_finalize_kernel<float, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rf3);
-  }
+  VFI_RF_ATTR(256, 1);
+  VFI_RF_ATTR(128, 1);
+  VFI_RF_ATTR(256, 2);
+#undef VFI_RF_ATTR
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return bail(fail(VFI_ERR_CUDA, std::string("kernel attribute setup: ") + cudaGetErrorString(e)));
   *out = idx;
@@ -441,7 +431,7 @@ int vfi_index_set_option(vfi_index_t* idx, int opt, int64_t value) {
       idx->opt_cta_pair = value;
       break;
     case VFI_OPT_TAIL:
-      if (value < 0 || value > 6) return fail(VFI_ERR_INVALID, "VFI_OPT_TAIL: 0 auto, 1 single-launch tail, 2 three-stage rescoring ring");
+      if (value < 0 || value > 3) return fail(VFI_ERR_INVALID, "VFI_OPT_TAIL: 0 auto, 1 single-launch tail, 2 128-byte pieces, 3 two-stage ring");
       idx->opt_tail = value;
       break;
     case VFI_OPT_CLUSTER:
@@ -750,35 +740,16 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
     LAUNCHED();
     VFI_CUDA(cudaGetLastError());
     const int threads = static_cast<int>(round_up(keep, 32));
-    const int stages = idx->opt_tail == 2 ? 3 : 2;
-    const size_t smem = vfi::rescore_finalize_smem(static_cast<int>(idx->dp), threads, stages);
-#define VFI_RF_LAUNCH(T, STAGES, PF, ROWS, PITCH)                                                                        \
-  vfi::rescore_finalize_kernel<T, STAGES, PF><<<nq, threads, smem, st>>>(                                                \
+#define VFI_RF_LAUNCH(T, P, S, ROWS, PITCH)                                                                              \
+  vfi::rescore_finalize_kernel<T, P, S><<<nq, threads, vfi::rescore_bulk_smem<P>(static_cast<int>(idx->dp), threads, S), st>>>( \
       idx->w_keys.as<uint64_t>(), idx->w_keys_n.as<uint32_t>(), idx->w_bound.as<float>(), keep, ROWS, PITCH,             \
       static_cast<int>(idx->dp), idx->w_qcanon.as<float>(), k, idx->id_offset, idx->w_eps.as<float>(), out_scores, out_ids, \
       d_flag + 1, d_flag, idx->d_max_err)
-#define VFI_RFB_LAUNCH(T, P, S, ROWS, PITCH)                                                                             \
-  vfi::rescore_finalize_bulk_kernel<T, P, S><<<nq, threads, vfi::rescore_bulk_smem<P>(static_cast<int>(idx->dp), threads, S), st>>>( \
-      idx->w_keys.as<uint64_t>(), idx->w_keys_n.as<uint32_t>(), idx->w_bound.as<float>(), keep, ROWS, PITCH,             \
-      static_cast<int>(idx->dp), idx->w_qcanon.as<float>(), k, idx->id_offset, idx->w_eps.as<float>(), out_scores, out_ids, \
-      d_flag + 1, d_flag, idx->d_max_err)
-    if (idx->opt_tail >= 4) {
-      const bool f32 = idx->store == VFI_STORE_F32;
-      if (idx->opt_tail == 4) { if (f32) VFI_RFB_LAUNCH(float, 128, 3, idx->master, idx->dp); else VFI_RFB_LAUNCH(uint16_t, 128, 3, idx->g, idx->kp); }
-      else if (idx->opt_tail == 5) { if (f32) VFI_RFB_LAUNCH(float, 256, 2, idx->master, idx->dp); else VFI_RFB_LAUNCH(uint16_t, 256, 2, idx->g, idx->kp); }
-      else { if (f32) VFI_RFB_LAUNCH(float, 128, 2, idx->master, idx->dp); else VFI_RFB_LAUNCH(uint16_t, 128, 2, idx->g, idx->kp); }
-    } else
-    if (idx->store == VFI_STORE_F32) {
-      if (stages == 3) VFI_RF_LAUNCH(float, 3, true, idx->master, idx->dp);
-      else if (idx->opt_tail == 3) VFI_RF_LAUNCH(float, 2, false, idx->master, idx->dp);
-      else VFI_RF_LAUNCH(float, 2, true, idx->master, idx->dp);
-    } else {
-      if (stages == 3) VFI_RF_LAUNCH(uint16_t, 3, true, idx->g, idx->kp);
-      else if (idx->opt_tail == 3) VFI_RF_LAUNCH(uint16_t, 2, false, idx->g, idx->kp);
-      else VFI_RF_LAUNCH(uint16_t, 2, true, idx->g, idx->kp);
-    }
+    const bool f32 = idx->store == VFI_STORE_F32;
+    if (idx->opt_tail == 2) { if (f32) VFI_RF_LAUNCH(float, 128, 1, idx->master, idx->dp); else VFI_RF_LAUNCH(uint16_t, 128, 1, idx->g, idx->kp); }
+    else if (idx->opt_tail == 3) { if (f32) VFI_RF_LAUNCH(float, 256, 2, idx->master, idx->dp); else VFI_RF_LAUNCH(uint16_t, 256, 2, idx->g, idx->kp); }
+    else { if (f32) VFI_RF_LAUNCH(float, 256, 1, idx->master, idx->dp); else VFI_RF_LAUNCH(uint16_t, 256, 1, idx->g, idx->kp); }
 #undef VFI_RF_LAUNCH
-#undef VFI_RFB_LAUNCH
     LAUNCHED();
     VFI_CUDA(cudaGetLastError());
   } else if (keep <= 256) {
