@@ -168,9 +168,16 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cpu, t_step = cpu_reference_arm(w, min(steps, 3), min(warmup, 1), args.cpu_rows, None)
+        # exactly K timed steps after W warm-ups; a step is one pass over a bounded row slice (--cpu-rows), scaled to the corpus.
+        # Bounded so the whole run ends within minutes whatever K is: at most ~120 s of CPU work.
+        rows = args.cpu_rows
+        est = 0.3 * (rows / 250_000) * (w["b"] / 1024)              # seconds per step on 16 host threads, measured on the pool
+        while rows > 20_000 and est * (steps + warmup) > 120:
+            rows //= 2
+            est /= 2
+        cpu, t_step = cpu_reference_arm(w, steps, warmup, rows, None)
         line = {"impl": "reference", "metric": "queries/sec", "value": cpu["value"], "unit": "queries/s", "n_gpus": args.gpus,
-                "steps": min(steps, 3), "warmup": min(warmup, 1), "ms_per_step": t_step * 1e3, "higher_is_better": True,
+                "steps": steps, "warmup": warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": cpu,
                 "e2e": {"value": cpu["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

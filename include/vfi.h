@@ -182,7 +182,8 @@ int vfi_bm25_create(const int64_t* indptr, const int32_t* indices, const float* 
 int vfi_bm25_destroy(vfi_bm25_t* b);
 int64_t vfi_bm25_ndocs(const vfi_bm25_t* b);
 /* q_tokens int32 [q_indptr[nq]] token ids in query order (unknown tokens already dropped,
- * repeats kept), q_indptr int64 [nq+1]. Scores accumulate in fp32 in query-token order. */
+ * repeats kept), q_indptr int64 [nq+1]: HOST arrays (they come from the host tokeniser). Scores accumulate
+ * in fp32 in query-token order. `mem` says where out_scores / out_ids live (VFI_MEM_HOST or VFI_MEM_DEVICE). */
 int vfi_bm25_search(vfi_bm25_t* b, const int32_t* q_tokens, const int64_t* q_indptr, int64_t nq,
                     int k, float* out_scores, int64_t* out_ids, int mem, void* stream);
 /* all n_docs scores of one query (host/device fp32 [n_docs]); serves retrieve(k = N) */

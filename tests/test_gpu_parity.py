@@ -310,6 +310,69 @@ def test_full_size_properties_c2(torch_cuda):
     idx.close()
 
 
+def test_full_size_properties_c3(torch_cuda):
+    """BASELINE config C3 on one GPU (10M x 1024 bf16, 1024 queries, top-100): size-independent properties.
+    (1) idempotence, total order, uniqueness; (2) the fused tcgen05 path equals the library's exhaustive canonical pass
+    (every row scored in fp64 order, exact selection) on a query subset; (3) two half-corpus shards merged by the
+    merge kernel equal the unsharded result bit for bit (the multi-GPU contract, on one device)."""
+    torch = torch_cuda
+    from veritasfi_b200 import _native as N, synth
+    from veritasfi_b200.dense import DenseIndex, merge_topk
+    dev = torch.device("cuda", 0)
+    free, _ = torch.cuda.mem_get_info(dev)
+    if free < 70 * (1 << 30):
+        pytest.skip("needs ~65 GB of free HBM")
+    n, d, b, k, chunk = 10_000_000, 1024, 1024, 100, 1 << 20
+    full = DenseIndex(d, store="bf16")
+    halves = [DenseIndex(d, store="bf16", id_offset=0), DenseIndex(d, store="bf16", id_offset=n // 2)]
+    full.reserve(n)
+    for h in halves:
+        h.reserve(n // 2)
+    probes = []
+    for c, r0 in enumerate(range(0, n, chunk)):
+        rows = synth.dense_corpus_torch(min(chunk, n - r0), d, 500 + c, dev)
+        if c == 0:
+            rows[2 * chunk // 3] = rows[chunk // 3]               # exact duplicate inside the first chunk: a planted tie
+        full.add(rows)
+        cut = max(0, min(rows.shape[0], n // 2 - r0))              # rows [0, cut) belong to the first half
+        if cut > 0:
+            halves[0].add(rows[:cut])
+        if cut < rows.shape[0]:
+            halves[1].add(rows[cut:])
+        if c in (0, 4, 9):
+            probes.append((r0 + chunk // 3, rows[chunk // 3].float().clone()))
+    q = synth.dense_queries_torch(b, d, 501, dev)
+    for j, (_, v) in enumerate(probes):
+        q[j] = v
+    ids, scores = full.search_batch(q, k)
+    ids2, scores2 = full.search_batch(q, k)
+    assert full.stats().last_path == N.PATH_FUSED
+    assert torch.equal(ids, ids2) and torch.equal(scores, scores2)
+    s, i = scores.cpu().numpy(), ids.cpu().numpy()
+    assert (i >= 0).all() and (i < n).all()
+    ds = np.diff(s, axis=1)
+    assert (ds <= 0).all() and (np.diff(i, axis=1)[ds == 0] > 0).all()
+    assert all(len(set(r)) == k for r in i)
+    for j, (row, _) in enumerate(probes):
+        assert i[j, 0] <= row and s[j, 0] >= 0.99
+    assert i[0, 0] == (1 << 20) // 3 and i[0, 1] == 2 * (1 << 20) // 3 and s[0, 0] == s[0, 1]   # the planted tie, lower id first
+    # (2) exhaustive canonical pass on a subset of the queries
+    sub = torch.cat([q[:4], q[500:504]])
+    full.set_option(N.OPT_FORCE_PATH, N.PATH_EXHAUSTIVE)
+    ie, se = full.search_batch(sub, k)
+    full.set_option(N.OPT_FORCE_PATH, 0)
+    pick = list(range(4)) + list(range(500, 504))
+    assert torch.equal(ie, ids[pick]) and torch.equal(se, scores[pick])
+    # (3) shard-merge == unsharded
+    parts = [h.search_batch(q, k) for h in halves]
+    gi = torch.stack([p[0] for p in parts])
+    gs = torch.stack([p[1] for p in parts])
+    mi, ms = merge_topk(gs, gi, k)
+    assert torch.equal(mi, ids) and torch.equal(ms, scores)
+    for x in [full] + halves:
+        x.close()
+
+
 # ------------------------------------------------------------------------------------------------ sparse
 @pytest.mark.parametrize("n_docs,n_vocab,nq,k,mean_len", [(3000, 500, 20, 10, 40), (50000, 5000, 64, 50, 40), (2048 * 3 + 5, 300, 9, 100, 12)])
 def test_bm25_matches_oracle(n_docs, n_vocab, nq, k, mean_len):

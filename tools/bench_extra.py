@@ -106,7 +106,7 @@ def c4s():
     gp.set_profile(True)
     mp = MultiPathRetriever(chunks, titles, t2c, gp, depth=L)
     q = synth.dense_queries_torch(B, d, 4100, DEV)
-    toks = synth.bm25_queries(B, V, 4300)
+    toks = GpuPostings.pack_tokens(synth.bm25_queries(B, V, 4300))
     for _ in range(2):
         mp.multipath_batch(q, None, toks, k, fusion="rrf")
     torch.cuda.synchronize()

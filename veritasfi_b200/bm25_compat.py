@@ -165,6 +165,31 @@ class GpuPostings:
                                              N.MEM_HOST, None))
         return ids, scores
 
+    def search_csr_device(self, toks: np.ndarray, qptr: np.ndarray, k: int, device=None):
+        """Same search with the results left on the GPU: (ids int64 [B,k], scores float32 [B,k]) torch CUDA tensors
+        (the hybrid path hands them straight to the fusion kernel)."""
+        import torch
+
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        B = len(qptr) - 1
+        toks = np.ascontiguousarray(toks, dtype=np.int32)
+        qptr = np.ascontiguousarray(qptr, dtype=np.int64)
+        scores = torch.full((B, k), -float(np.finfo(np.float32).max), dtype=torch.float32, device=dev)
+        ids = torch.full((B, k), -1, dtype=torch.int64, device=dev)
+        if B:
+            N.check(N.load().vfi_bm25_search(self._h, toks.ctypes.data_as(C.c_void_p), qptr.ctypes.data_as(C.c_void_p),
+                                             B, int(k), C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()),
+                                             N.MEM_DEVICE, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        return ids, scores
+
+    @staticmethod
+    def pack_tokens(token_lists: Sequence[Sequence[int]]):
+        """Per-query token id lists -> (toks int32 [total], qptr int64 [B+1]) as vfi_bm25_search takes them."""
+        qptr = np.zeros(len(token_lists) + 1, dtype=np.int64)
+        np.cumsum([len(t) for t in token_lists], out=qptr[1:])
+        toks = np.fromiter((t for lst in token_lists for t in lst), dtype=np.int32, count=int(qptr[-1]))
+        return toks, qptr
+
     def score_all(self, tokens: Sequence[int]) -> np.ndarray:
         toks = np.ascontiguousarray(tokens, dtype=np.int32)
         out = np.zeros(self.n_docs, dtype=np.float32)

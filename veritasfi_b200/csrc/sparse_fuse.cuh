@@ -324,16 +324,23 @@ __global__ void __launch_bounds__(kBmThreads, 4) bm25_kernel(const Bm25Params p)
 }
 
 // When fewer than k docs matched (all-positive impacts), the remaining places go to the lowest
-// ids among the docs with score exactly 0.  One thread per query; k is small.
+// ids among the docs with score exactly 0.  One warp per query: the 32 lanes count the matched places together (rows
+// are padded with id -1 after the last match); the fill itself is rare and short, lane 0 does it.
 __global__ void bm25_zero_fill_kernel(float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
                                       int nq, int k, int64_t n_docs, int64_t id_offset) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (q >= nq) return;
   float* sc = out_scores + static_cast<int64_t>(q) * k;
   int64_t* id = out_ids + static_cast<int64_t>(q) * k;
-  int n = 0;
-  while (n < k && id[n] >= 0) ++n;
-  const int matched = n;
+  int matched = 0;
+  for (int base = 0; base < k; base += 32) {
+    const int i = base + lane;
+    const bool has = i < k && id[i] >= 0;
+    matched += __popc(__ballot_sync(0xFFFFFFFFu, has));
+  }
+  if (matched >= k || lane != 0) return;
+  int n = matched;
   int64_t cand = 0;
   while (n < k && cand < n_docs) {
     bool used = false;

@@ -734,9 +734,16 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
     VFI_TRY(idx->w_keys.ensure(static_cast<size_t>(nq) * keep * 8));
     VFI_TRY(idx->w_keys_n.ensure(static_cast<size_t>(nq) * 4));
     VFI_TRY(idx->w_bound.ensure(static_cast<size_t>(nq) * 4));
-    vfi::cand_reduce_kernel<vfi::CandSmem><<<nq, 256, sizeof(vfi::CandSmem), st>>>(idx->w_cand.as<uint64_t>(), idx->w_cand_count.as<uint32_t>(),
-                                                                     n_groups, nq_pad, cap, keep, tau, idx->w_keys.as<uint64_t>(),
-                                                                     idx->w_keys_n.as<uint32_t>(), idx->w_bound.as<float>());
+    // about 16 k' keys reach this kernel per query: up to k' = 128 they fit the light 1024-key selection buffer's fast
+    // paths (seven CTAs per SM); above that the 4096-key buffer avoids the radix walk over global memory
+    if (keep <= 128)
+      vfi::cand_reduce_kernel<vfi::CandSmem><<<nq, 256, sizeof(vfi::CandSmem), st>>>(
+          idx->w_cand.as<uint64_t>(), idx->w_cand_count.as<uint32_t>(), n_groups, nq_pad, cap, keep, tau, idx->w_keys.as<uint64_t>(),
+          idx->w_keys_n.as<uint32_t>(), idx->w_bound.as<float>());
+    else
+      vfi::cand_reduce_kernel<vfi::SelectSmem><<<nq, 256, sizeof(vfi::SelectSmem), st>>>(
+          idx->w_cand.as<uint64_t>(), idx->w_cand_count.as<uint32_t>(), n_groups, nq_pad, cap, keep, tau, idx->w_keys.as<uint64_t>(),
+          idx->w_keys_n.as<uint32_t>(), idx->w_bound.as<float>());
     LAUNCHED();
     VFI_CUDA(cudaGetLastError());
     const int threads = static_cast<int>(round_up(keep, 32));
@@ -1447,7 +1454,8 @@ int vfi_bm25_search(vfi_bm25_t* b, const int32_t* q_tokens, const int64_t* q_ind
   if (k <= 0) return fail(VFI_ERR_INVALID, "k must be positive");
   if (k > VFI_MAX_K / 2) return fail(VFI_ERR_UNSUPPORTED, "bm25 top-k supports k <= 1024 (use vfi_bm25_score_all for k = N)");
   if (nq == 0) return VFI_OK;
-  if (mem != VFI_MEM_HOST) return fail(VFI_ERR_UNSUPPORTED, "vfi_bm25_search takes host token buffers and host outputs");
+  if (mem != VFI_MEM_HOST && mem != VFI_MEM_DEVICE) return fail(VFI_ERR_INVALID, "vfi_bm25_search: mem must be VFI_MEM_HOST or VFI_MEM_DEVICE");
+  const bool dev_out = mem == VFI_MEM_DEVICE;   // token buffers are host memory either way; `mem` says where the outputs live
   std::lock_guard<std::mutex> lock(b->mu);
   DeviceGuard guard(b->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1481,8 +1489,12 @@ int vfi_bm25_search(vfi_bm25_t* b, const int32_t* q_tokens, const int64_t* q_ind
   VFI_TRY(b->w_keys.ensure(static_cast<size_t>(nq) * keep * 8));
   VFI_TRY(b->w_keys_n.ensure(static_cast<size_t>(nq) * 4));
   VFI_TRY(b->w_bound.ensure(static_cast<size_t>(nq) * 4));
-  VFI_TRY(b->w_out_scores.ensure(static_cast<size_t>(nq) * k * 4));
-  VFI_TRY(b->w_out_ids.ensure(static_cast<size_t>(nq) * k * 8));
+  if (!dev_out) {
+    VFI_TRY(b->w_out_scores.ensure(static_cast<size_t>(nq) * k * 4));
+    VFI_TRY(b->w_out_ids.ensure(static_cast<size_t>(nq) * k * 8));
+  }
+  float* d_scores = dev_out ? out_scores : b->w_out_scores.as<float>();
+  int64_t* d_ids = dev_out ? out_ids : b->w_out_ids.as<int64_t>();
   VFI_TRY(b->w_ctr.ensure(16 + static_cast<size_t>(nq) * 8));
   if (n_tok > 0) VFI_CUDA(cudaMemcpyAsync(b->w_tok.p, q_tokens, static_cast<size_t>(n_tok) * 4, cudaMemcpyHostToDevice, st));
   VFI_CUDA(cudaMemcpyAsync(b->w_qptr.p, q_indptr, static_cast<size_t>(nq + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -1520,16 +1532,19 @@ int vfi_bm25_search(vfi_bm25_t* b, const int32_t* q_tokens, const int64_t* q_ind
   LAUNCHED();
   vfi::finalize_kernel<<<static_cast<unsigned>(nq), 256, sizeof(vfi::SelectSmem), st>>>(
       b->w_keys.as<uint64_t>(), keep, keep, nullptr, b->w_keys_n.as<uint32_t>(), k, b->id_offset, nullptr, nullptr, 0,
-      b->w_out_scores.as<float>(), b->w_out_ids.as<int64_t>(), nullptr, nullptr);
+      d_scores, d_ids, nullptr, nullptr);
   LAUNCHED();
   if (b->all_positive) {
-    vfi::bm25_zero_fill_kernel<<<static_cast<unsigned>(ceil_div(nq, 128)), 128, 0, st>>>(
-        b->w_out_scores.as<float>(), b->w_out_ids.as<int64_t>(), static_cast<int>(nq), k, b->n_docs, b->id_offset);
+    vfi::bm25_zero_fill_kernel<<<static_cast<unsigned>(ceil_div(nq, 4)), 128, 0, st>>>(
+        d_scores, d_ids, static_cast<int>(nq), k, b->n_docs, b->id_offset);
     LAUNCHED();
   }
   VFI_CUDA(cudaGetLastError());
-  VFI_CUDA(cudaMemcpyAsync(out_scores, b->w_out_scores.p, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));
-  VFI_CUDA(cudaMemcpyAsync(out_ids, b->w_out_ids.p, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, st));
+  if (!dev_out) {
+    VFI_CUDA(cudaMemcpyAsync(out_scores, d_scores, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));
+    VFI_CUDA(cudaMemcpyAsync(out_ids, d_ids, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, st));
+  }
+  // the token staging buffers are reused by the next call and the host token arrays may be freed by the caller: wait
   VFI_CUDA(cudaStreamSynchronize(st));
   if (b->profile) {
     float ms = 0.f;

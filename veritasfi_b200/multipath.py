@@ -40,9 +40,11 @@ class MultiPathRetriever:
             lists_i.append(di)
             lists_s.append(ds)
         if self.postings is not None:
-            bi, bs = self.postings.search(tokens, L)
-            lists_i.append(torch.from_numpy(bi).to(dev))
-            lists_s.append(torch.from_numpy(bs).to(dev))
+            # tokens: per-query id lists, or the packed (toks int32, qptr int64) pair of GpuPostings.pack_tokens
+            toks, qptr = tokens if isinstance(tokens, tuple) else GpuPostings.pack_tokens(tokens)
+            bi, bs = self.postings.search_csr_device(toks, qptr, L, dev)     # results stay in HBM for the fusion kernel
+            lists_i.append(bi)
+            lists_s.append(bs)
         ids = torch.stack(lists_i, dim=1).contiguous()
         scores = torch.stack(lists_s, dim=1).contiguous()
         if fusion == "rrf":
