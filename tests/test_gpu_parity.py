@@ -432,6 +432,35 @@ def test_bm25_general_impacts_and_doc_shards():
     assert (mi == I0).all() and (ms == S0).all()
 
 
+@pytest.mark.parametrize("k,n_docs,id_offset", [(64, 5000, 0), (200, 5000, 1000), (1000, 1500, 7), (32, 20, 0)])
+def test_bm25_queries_matching_fewer_than_k_docs_are_filled_with_the_lowest_zero_score_ids(k, n_docs, id_offset, torch_cuda):
+    """bm25s scores every doc, so a query that matches m < k docs gets the k - m lowest-id docs of score exactly 0 after
+    them (total order: score desc, id asc).  Rare tokens + large k exercise that fill, host and device outputs."""
+    torch = torch_cuda
+    from oracle import bm25 as obm
+    from veritasfi_b200.bm25_compat import GpuPostings
+    rng = np.random.default_rng(k)
+    n_vocab = 60
+    # token t occurs in t+1 random docs (token 0 in one doc ... token 59 in sixty), positive impacts
+    docs = [np.sort(rng.choice(n_docs, size=min(n_docs, t + 1), replace=False)) for t in range(n_vocab)]
+    docs[3] = np.unique(np.concatenate([[0, 1], docs[3]]))               # low ids among the matches: the fill must skip them
+    indptr = np.zeros(n_vocab + 1, np.int64)
+    np.cumsum([len(x) for x in docs], out=indptr[1:])
+    indices = np.concatenate(docs).astype(np.int32)
+    data = rng.uniform(0.1, 3.0, size=len(indices)).astype(np.float32)
+    qs = [[0], [3, 5], [59, 58, 57], [10, 10, 2], [], [1, 30, 44, 7]]
+    kk = min(k, n_docs)
+    I0, S0 = obm.retrieve(indptr, indices, data, qs, n_docs, kk)
+    gp = GpuPostings(indptr, indices, data, n_docs, id_offset=id_offset)
+    I, S = gp.search(qs, kk)
+    assert (I == I0 + id_offset).all() and (S == S0).all()
+    toks, qptr = GpuPostings.pack_tokens(qs)
+    Id, Sd = gp.search_csr_device(toks, qptr, kk)
+    assert (Id.cpu().numpy() == I0 + id_offset).all() and (Sd.cpu().numpy() == S0).all()
+    assert (S0[:, -1] == 0).sum() >= 3                                   # several queries really needed the fill
+    gp.close()
+
+
 def test_bm25_rejects_malformed_postings():
     from veritasfi_b200 import _native as N
     from veritasfi_b200.bm25_compat import GpuPostings

@@ -323,13 +323,15 @@ __global__ void __launch_bounds__(kBmThreads, 4) bm25_kernel(const Bm25Params p)
   }
 }
 
-// When fewer than k docs matched (all-positive impacts), the remaining places go to the lowest
-// ids among the docs with score exactly 0.  One warp per query: the 32 lanes count the matched places together (rows
-// are padded with id -1 after the last match); the fill itself is rare and short, lane 0 does it.
-__global__ void bm25_zero_fill_kernel(float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
-                                      int nq, int k, int64_t n_docs, int64_t id_offset) {
-  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+// When fewer than k docs matched (all-positive impacts), the remaining places go to the lowest ids among the docs
+// with score exactly 0.  One warp per query (4 per CTA), k <= 1024: the lanes count the matched places together (rows are
+// padded with id -1 after the last match); the missing places can only be ids below k, so the matched ids below k are
+// marked in a 1024-bit map (one word per lane) and every lane emits the free ids of its word at the scanned position.
+__global__ void __launch_bounds__(128) bm25_zero_fill_kernel(float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+                                                             int nq, int k, int64_t n_docs, int64_t id_offset) {
+  __shared__ uint32_t bitmap[4][32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 4 + w;
   if (q >= nq) return;
   float* sc = out_scores + static_cast<int64_t>(q) * k;
   int64_t* id = out_ids + static_cast<int64_t>(q) * k;
@@ -339,14 +341,32 @@ __global__ void bm25_zero_fill_kernel(float* __restrict__ out_scores, int64_t* _
     const bool has = i < k && id[i] >= 0;
     matched += __popc(__ballot_sync(0xFFFFFFFFu, has));
   }
-  if (matched >= k || lane != 0) return;
-  int n = matched;
-  int64_t cand = 0;
-  while (n < k && cand < n_docs) {
-    bool used = false;
-    for (int i = 0; i < matched; ++i) used |= (id[i] - id_offset == cand);
-    if (!used) { id[n] = cand + id_offset; sc[n] = 0.f; ++n; }
-    ++cand;
+  if (matched >= k) return;
+  bitmap[w][lane] = 0u;
+  __syncwarp();
+  for (int i = lane; i < matched; i += 32) {
+    const int64_t v = id[i] - id_offset;
+    if (v >= 0 && v < k) atomicOr(&bitmap[w][v >> 5], 1u << (v & 31));
+  }
+  __syncwarp();
+  const int64_t limit = min(static_cast<int64_t>(k), n_docs);      // candidate ids 0 .. limit-1
+  const int64_t first = static_cast<int64_t>(lane) * 32;
+  uint32_t valid = 0u;
+  if (first < limit) valid = (limit - first >= 32) ? 0xFFFFFFFFu : ((1u << (limit - first)) - 1u);
+  uint32_t free_bits = ~bitmap[w][lane] & valid;
+  int incl = __popc(free_bits);
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  int pos = matched + incl - __popc(free_bits);
+  while (free_bits != 0u && pos < k) {
+    const int b = __ffs(free_bits) - 1;
+    free_bits &= free_bits - 1u;
+    id[pos] = first + b + id_offset;
+    sc[pos] = 0.f;
+    ++pos;
   }
 }
 
