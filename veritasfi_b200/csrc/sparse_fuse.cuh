@@ -29,7 +29,7 @@ constexpr int kBmThreads = 256;
 constexpr int kBmMaxTok = 64;     // tokens per query handled by the kernel
 constexpr int kBmMaxRanges = 8;   // ranges per segment
 constexpr int kBmScan = 1024;     // docs scanned between buffer-compaction checks
-constexpr int kBmUnroll = 16;     // postings per thread in flight while a heavy token streams
+constexpr int kBmUnroll = 8;      // postings per thread in flight while a heavy token streams
 constexpr int kBmLight = 8;       // light postings per thread prefetched per range (all light tokens at once)
 
 struct Bm25Params {
@@ -55,11 +55,11 @@ struct Bm25Params {
 struct Bm25Smem {
   float acc[kBmRange];
   int64_t offs[kBmMaxTok][kBmMaxRanges + 1];   // posting offset of token t at range boundary r
-  uint32_t pref[kBmMaxTok + 1];                // exclusive prefix of the per-token posting counts of the current range
-  uint32_t lstart[kBmMaxTok];                  // flat start of token t among the prefetched light tokens, or ~0
-  uint32_t lpre[kBmMaxTok + 1];                // the same starts, compacted over the light tokens only
-  uint8_t ltok[kBmMaxTok];                     // token index of the i-th light token
+  uint32_t cnt[kBmMaxTok];                     // postings of token t in the current range
+  uint8_t kind[kBmMaxTok];                     // 0 none here, 1 light (prefetched, one posting per thread), 2 streamed
+  uint8_t ltok[kBmLight + 1];                  // token index of the u-th light token (ascending), padded with T
   int n_light;
+  uint32_t total;
   uint32_t overflow;
   uint32_t count;
   uint64_t tau;
@@ -111,116 +111,110 @@ __global__ void __launch_bounds__(kBmThreads, 4) bm25_kernel(const Bm25Params p)
       const int64_t rs = d0 + static_cast<int64_t>(r) * kBmRange;
       const int64_t re = min(rs + kBmRange, d1);
       const int range_docs = static_cast<int>(re - rs);
-      if (tid == 0) {
-        uint32_t run = 0;
-        for (int t = 0; t < T; ++t) {
-          sm->pref[t] = run;
-          run += static_cast<uint32_t>(sm->offs[t][r + 1] - sm->offs[t][r]);
+      // Per-range bookkeeping by warp 0 (T <= 64: two tokens per lane): posting counts, light/streamed classification
+      // by ballot, the first kBmLight light tokens in token order.  A light token has at most kBmThreads postings in the
+      // range: thread i prefetches its i-th posting, all light tokens at once, so their latencies overlap; heavier
+      // tokens (and light ones beyond kBmLight) are streamed when their turn comes.
+      if (tid < 32) {
+        uint32_t sum = 0;
+        uint32_t light_before = 0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int t = half * 32 + static_cast<int>(tid);
+          const uint32_t c = (t < T) ? static_cast<uint32_t>(sm->offs[t][r + 1] - sm->offs[t][r]) : 0u;
+          const bool light = c > 0 && c <= static_cast<uint32_t>(kBmThreads);
+          const uint32_t lmask = __ballot_sync(0xFFFFFFFFu, light);
+          const uint32_t ord = light_before + __popc(lmask & ((1u << tid) - 1u));
+          if (t < T) {
+            sm->cnt[t] = c;
+            sm->kind[t] = (c == 0) ? 0 : ((light && ord < static_cast<uint32_t>(kBmLight)) ? 1 : 2);
+            if (light && ord < static_cast<uint32_t>(kBmLight)) sm->ltok[ord] = static_cast<uint8_t>(t);
+          }
+          light_before += __popc(lmask);
+          sum += c;
         }
-        sm->pref[T] = run;
-        if (p.qtau != nullptr) {     // adopt a better threshold published by another segment of this query
-          const uint64_t g = *reinterpret_cast<volatile unsigned long long*>(p.qtau + q);
-          if (g > sm->tau) sm->tau = g;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        if (tid == 0) {
+          sm->total = sum;
+          sm->n_light = static_cast<int>(min(light_before, static_cast<uint32_t>(kBmLight)));
+          sm->overflow = 0;
+          if (p.qtau != nullptr) {     // adopt a better threshold published by another segment of this query
+            const uint64_t g = *reinterpret_cast<volatile unsigned long long*>(p.qtau + q);
+            if (g > sm->tau) sm->tau = g;
+          }
         }
       }
       __syncthreads();
-      const uint32_t total = sm->pref[T];
-      if (total == 0 && p.all_positive && p.dump == nullptr) {   // no token touches this range
-        __syncthreads();                                           // (everyone has read pref before it is rewritten)
+      if (sm->total == 0 && p.all_positive && p.dump == nullptr) {   // no token touches this range
+        __syncthreads();                                               // (everyone has read total before it is rewritten)
         continue;
       }
-
-      // Light tokens (<= 256 postings here) would each expose a full memory latency for a handful of
-      // postings: the light tokens' postings form one flat token-major sequence of at most
-      // 256 x kBmLight entries that is loaded up front with every load in flight.  Heavier tokens
-      // (and light ones beyond that capacity) are streamed when their turn comes.
-      constexpr uint32_t kLightCap = kBmThreads * kBmLight;
-      auto cnt_of = [&](int t) -> uint32_t { return sm->pref[t + 1] - sm->pref[t]; };
-      if (tid == 0) {
-        uint32_t run = 0;
-        int nl = 0;
-        for (int t = 0; t < T; ++t) {
-          const uint32_t c = cnt_of(t);
-          if (c > 0 && c <= 256u && run + c <= kLightCap) {
-            sm->lstart[t] = run;
-            sm->ltok[nl] = static_cast<uint8_t>(t);
-            sm->lpre[nl] = run;
-            ++nl;
-            run += c;
-          } else {
-            sm->lstart[t] = 0xFFFFFFFFu;
-          }
-        }
-        sm->lpre[nl] = run;
-        sm->n_light = nl;
-        sm->overflow = 0;
-      }
-      __syncthreads();
-      const uint32_t ltotal = sm->lpre[sm->n_light];
+      const int n_light = sm->n_light;
       int32_t ldoc[kBmLight];
       float lval[kBmLight];
-      int ltk[kBmLight];
 #pragma unroll
       for (int u = 0; u < kBmLight; ++u) {
-        const uint32_t j = u * kBmThreads + tid;
-        ltk[u] = -1;
-        ldoc[u] = 0;
+        ldoc[u] = -1;
         lval[u] = 0.f;
-        if (j < ltotal) {
-          int lo = 0, hi = sm->n_light;            // largest i with lpre[i] <= j
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (sm->lpre[mid] <= j) lo = mid; else hi = mid;
+        if (u < n_light) {
+          const int t = sm->ltok[u];
+          if (tid < sm->cnt[t]) {
+            const int64_t o = sm->offs[t][r] + tid;
+            ldoc[u] = __ldg(p.indices + o);
+            lval[u] = __ldg(p.data + o);
           }
-          const int t = sm->ltok[lo];
-          const int64_t o = sm->offs[t][r] + (j - sm->lpre[lo]);
-          ltk[u] = t;
-          ldoc[u] = __ldg(p.indices + o);
-          lval[u] = __ldg(p.data + o);
         }
       }
       float* acc = sm->acc - rs;                    // acc[doc] for docs of this range
-      for (int t = 0; t < T; ++t) {
-        const uint32_t n = cnt_of(t);
-        if (n == 0) continue;
-        if (sm->lstart[t] != 0xFFFFFFFFu) {
+      // Stream one token: coalesced 4-byte loads, kBmUnroll postings per thread in flight; adjacent lanes hold ADJACENT
+      // postings, i.e. ascending (for heavy tokens consecutive) docs, so the read-modify-write of the accumulator is
+      // free of bank conflicts.  Inside one token every doc occurs once: the adds of different threads never collide.
+      auto stream = [&](int t) {
+        const uint32_t n = sm->cnt[t];
+        const int32_t* ip = p.indices + sm->offs[t][r] + tid;
+        const float* dp = p.data + sm->offs[t][r] + tid;
+        uint32_t i = tid;
+        for (; i + (kBmUnroll - 1) * kBmThreads < n; i += kBmUnroll * kBmThreads) {
+          int32_t dd[kBmUnroll];
+          float vv[kBmUnroll];
 #pragma unroll
-          for (int u = 0; u < kBmLight; ++u)
-            if (ltk[u] == t) acc[ldoc[u]] += lval[u];
-        } else {
-          // stream: 16-byte loads over the aligned middle, scalar head and tail.  Inside one token every
-          // doc occurs once, so the plain read-modify-write of different threads never collide.
-          const int64_t o0 = sm->offs[t][r];
-          const int32_t* ip = p.indices + o0;
-          const float* dp = p.data + o0;
-          const uint32_t head = min(n, static_cast<uint32_t>((4 - (o0 & 3)) & 3));
-          const uint32_t nvec = (n - head) >> 2;
-          if (tid < head) acc[__ldg(ip + tid)] += __ldg(dp + tid);
-          const int4* ip4 = reinterpret_cast<const int4*>(ip + head);
-          const float4* dp4 = reinterpret_cast<const float4*>(dp + head);
-          for (uint32_t base = 0; base < nvec; base += kBmThreads * 4) {
-            int4 d4[4];
-            float4 v4[4];
+          for (int u = 0; u < kBmUnroll; ++u) { dd[u] = __ldg(ip + u * kBmThreads); vv[u] = __ldg(dp + u * kBmThreads); }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const uint32_t i = base + u * kBmThreads + tid;
-              if (i < nvec) { d4[u] = __ldg(ip4 + i); v4[u] = __ldg(dp4 + i); }
-              else { d4[u] = make_int4(-1, -1, -1, -1); v4[u] = make_float4(0.f, 0.f, 0.f, 0.f); }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (d4[u].x >= 0) {
-                acc[d4[u].x] += v4[u].x;
-                acc[d4[u].y] += v4[u].y;
-                acc[d4[u].z] += v4[u].z;
-                acc[d4[u].w] += v4[u].w;
-              }
-            }
-          }
-          const uint32_t tail0 = head + (nvec << 2);
-          if (tail0 + tid < n) acc[__ldg(ip + tail0 + tid)] += __ldg(dp + tail0 + tid);
+          for (int u = 0; u < kBmUnroll; ++u) acc[dd[u]] += vv[u];
+          ip += kBmUnroll * kBmThreads;
+          dp += kBmUnroll * kBmThreads;
         }
-        __syncthreads();    // token t fully applied before token t+1 touches the same docs
+        if (i < n) {
+          int32_t dd[kBmUnroll];
+          float vv[kBmUnroll];
+#pragma unroll
+          for (int u = 0; u < kBmUnroll; ++u) {
+            dd[u] = -1;
+            vv[u] = 0.f;
+            if (i + u * kBmThreads < n) { dd[u] = __ldg(ip + u * kBmThreads); vv[u] = __ldg(dp + u * kBmThreads); }
+          }
+#pragma unroll
+          for (int u = 0; u < kBmUnroll; ++u)
+            if (dd[u] >= 0) acc[dd[u]] += vv[u];
+        }
+      };
+      // tokens in query order, a block barrier after each (token t fully applied before token t+1 touches the same
+      // docs): the prefetched light tokens are walked by a compile-time index, streamed tokens in between
+      {
+        int t = 0;
+#pragma unroll
+        for (int u = 0; u <= kBmLight; ++u) {
+          const int tl = (u < n_light) ? static_cast<int>(sm->ltok[u < kBmLight ? u : 0]) : T;
+          for (; t < tl; ++t) {
+            if (sm->kind[t] == 2) { stream(t); __syncthreads(); }
+          }
+          if (u < kBmLight && u < n_light) {
+            if (ldoc[u] >= 0) acc[ldoc[u]] += lval[u];
+            __syncthreads();
+            t = tl + 1;
+          }
+        }
       }
 
       if (p.dump != nullptr) {
