@@ -131,3 +131,27 @@ def test_world_size_2_gloo_allgather_merge_equals_unsharded(tmp_path):
     out = str(tmp_path / "res")
     mp.spawn(_gloo_worker, args=(2, port, 301, 24, 9, out), nprocs=2, join=True)
     assert open(out + ".0").read() == "ok" and open(out + ".1").read() == "ok"
+
+
+def test_bench_reference_arm_prints_the_contract_line_and_the_gpu_arm_refuses_to_run_without_a_device():
+    """`bench.py --impl reference` times the CPU port of the reference's path (no GPU needed) and prints ONE JSON line with
+    the keys the driver reads; the default arm has no CPU fallback."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "small", "--steps", "2",
+                        "--warmup", "0", "--cpu-rows", "20000"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "queries/sec" and d["unit"] == "queries/s" and d["higher_is_better"] is True
+    assert d["steps"] == 2 and d["warmup"] == 0 and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    import torch
+    if not torch.cuda.is_available():
+        p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--workload", "small", "--steps", "1"], capture_output=True,
+                           text=True, timeout=300)
+        assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
