@@ -269,9 +269,9 @@ struct CanonCfg {
 
 // Canonical scores of 32 rows against one query: lane l owns row `id` (valid or not).  my_tile: 32*kCanonPitch
 // words, my_qs: CanonCfg<RowT>::kElems doubles, both private to the calling warp.  All 32 lanes must call.
-// Measured on B200 (profiles/r1_tail_conv.md): vector fp64 issues at ~2 lanes/clk/SM, so the DFMA chain is the
-// floor of this routine (16 SM-cycles per warp-wide DFMA); widening the stored values with integer instructions
-// instead of F2F.F64.F32 cost 17 ALU instructions per element and was slower (300 vs 232 us for 1024 x 128 rows).
+// Used by the exhaustive pass, by the k' > 256 tail and by the single-launch tail (VFI_OPT_TAIL=1).  One warp walking 32 rows is
+// latency-bound on the 12-cycle dependent DFMA chain plus the F2F.F64.F32 conversions (16 lanes/clk/SM), not on the fp64 pipe (64 lanes/clk/SM,
+// tools/ubench/fp64_rates.cu): it needs many resident warps, which is why the k' <= 256 tail has its own thread-per-candidate kernel below.
 template <typename RowT>
 __device__ __forceinline__ float canon_dot_warp(const RowT* __restrict__ rows, int64_t row_pitch, int dp,
                                                 const float* __restrict__ qv, uint32_t id, bool valid,
