@@ -154,6 +154,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hint", type=int, default=1)
     ap.add_argument("--tail", type=int, default=0, help="VFI_OPT_TAIL (0 default: selection kernel + bulk-copy rescoring kernel, 1 single-launch tail, 2/3 variants)")
+    ap.add_argument("--sync", action="store_true",
+                    help="N=1: one synchronous search per step instead of two batches in flight (search_begin/search_finish)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: fused peer-memory push+merge kernel over NVLink, or NCCL all-gather + merge kernel")
     args = ap.parse_args()
@@ -223,6 +225,26 @@ def main():
     def step_device():
         return searcher.search(q_dev, w["k"])
 
+    pipelined = world == 1 and not args.sync
+    config["pipeline"] = ("two batches in flight: vfi_index_search_begin(i+1) is enqueued before vfi_index_search_finish(i) reads the "
+                          "certificate flag of batch i" if pipelined else "one synchronous search (+ exchange) per step")
+
+    def run_device_steps(k_steps):
+        """K steps of the hot path with inputs resident in HBM.  N=1: a serving loop keeps two batches in flight so the GPU does
+        not idle while the host looks at the certificate flag; every batch is still certified (and repaired if needed) inside
+        the timed region.  N>1: local search, then the exchange, synchronously per batch."""
+        if not pipelined:
+            for _ in range(k_steps):
+                step_device()
+            return
+        prev = None
+        for _ in range(k_steps):
+            t = index.search_begin(q_dev, w["k"])
+            if prev is not None:
+                index.search_finish(prev)
+            prev = t
+        index.search_finish(prev)
+
     def step_e2e():
         if world == 1:   # the reference-facing host call of the C ABI: H2D, search, D2H inside
             index.search_host_into(q_pin.data_ptr(), w["b"], w["k"], out_s_pin.data_ptr(), out_i_pin.data_ptr())
@@ -233,15 +255,18 @@ def main():
             out_s_pin.copy_(scores, non_blocking=True)
             torch.cuda.synchronize()
 
-    def timed(fn, k_steps):
+    def timed(fn, k_steps, block=False):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        for _ in range(k_steps):
-            fn()
+        if block:
+            fn(k_steps)
+        else:
+            for _ in range(k_steps):
+                fn()
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -253,8 +278,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(warmup):
-        step_device()
+    run_device_steps(warmup)
     for _ in range(min(warmup, 3)):
         step_e2e()
     if os.environ.get("VFI_BENCH_BREAKDOWN"):
@@ -286,7 +310,7 @@ def main():
         sampler.start()
         sampler.wait_first()
     launches0 = N.launch_count()
-    ms_total = timed(step_device, steps)
+    ms_total = timed(run_device_steps, steps, block=True)
     launches = N.launch_count() - launches0
     st = index.stats()
     clocks = sampler.stop() if rank == 0 else None

@@ -99,6 +99,15 @@ int vfi_index_pairwise(vfi_index_t* idx, const int64_t* ids, int n, float* out, 
 int vfi_index_search(vfi_index_t* idx, const float* q, int64_t nq, int k, float* out_scores,
                      int64_t* out_ids, int mem, void* stream);
 
+/* Pipelined form for device buffers: begin() enqueues one batch (nq <= 1024) on `stream` and returns at once with a
+ * ticket; finish(ticket) waits for that batch, checks its exactness certificate and repairs the rare query that failed it,
+ * after which out_scores / out_ids hold the same bits vfi_index_search would have produced.  Up to 4 batches may be in
+ * flight per index, all on the same stream; q and the output buffers must stay valid until finish.  A serving loop that
+ * begins batch i+1 before finishing batch i never leaves the GPU idle during the host's look at the certificate flag. */
+int vfi_index_search_begin(vfi_index_t* idx, const float* q, int64_t nq, int k, float* out_scores,
+                           int64_t* out_ids, void* stream, int* ticket);
+int vfi_index_search_finish(vfi_index_t* idx, int ticket);
+
 /* tuning / introspection ------------------------------------------------------------------ */
 enum {
   VFI_OPT_OVERFETCH = 1,     /* candidates kept per query by the tensor-core pass (0 = auto) */

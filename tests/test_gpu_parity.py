@@ -178,6 +178,40 @@ def test_cta_pair_kernel_matches_oracle_and_the_single_cta_kernel(torch_cuda, nq
     idx.close()
 
 
+@pytest.mark.parametrize("hint", [1, 2])
+def test_pipelined_search_begin_finish_equals_the_synchronous_search(torch_cuda, hint):
+    """Batches enqueued back to back with search_begin and collected later give the bits of the synchronous call, also
+    when every certificate fails (hint = 2 admits nothing) and the repair of batch i runs after batch i+1 was launched."""
+    torch = torch_cuda
+    from oracle import flat_ip
+    from veritasfi_b200 import _native as N
+    from veritasfi_b200.dense import DenseIndex
+    n, d, k = 30000, 256, 20
+    xb, _ = _world(n, d, 4, 21, True)
+    idx = DenseIndex(d, store="bf16")
+    idx.add(xb)
+    idx.set_option(N.OPT_FORCE_PATH, N.PATH_FUSED)
+    idx.set_option(N.OPT_TAU_HINT, hint)
+    from veritasfi_b200 import synth
+    batches = [torch.from_numpy(synth.dense_queries_np(nq, d, 100 + j, xb)).cuda() for j, nq in enumerate([33, 130, 7, 64, 256])]
+    want = [flat_ip.search(flat_ip.bf16_round(b.cpu().numpy()), flat_ip.bf16_round(xb), k) for b in batches]
+    tickets = [idx.search_begin(b, k) for b in batches[:4]]            # four in flight (the maximum)
+    with pytest.raises(N.VfiError):
+        idx.search_begin(batches[4], k)                               # a fifth is refused until a ticket is finished
+    got = [idx.search_finish(t) for t in tickets[:2]]
+    tickets.append(idx.search_begin(batches[4], k))
+    got += [idx.search_finish(t) for t in tickets[2:]]
+    for (ids, scores), (D0, I0) in zip(got, want):
+        assert (ids.cpu().numpy() == I0).all() and (scores.cpu().numpy() == D0).all()
+    with pytest.raises(N.VfiError):
+        idx.search_finish(tickets[0])                                 # already collected
+    ids, scores = idx.search_batch(batches[1], k)                     # the synchronous call still works afterwards
+    assert (ids.cpu().numpy() == want[1][1]).all()
+    if hint == 2:
+        assert idx.stats().retried_queries > 0
+    idx.close()
+
+
 def test_ties_duplicates_zero_rows_and_padding(torch_cuda):
     torch = torch_cuda
     from oracle import flat_ip

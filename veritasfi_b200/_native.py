@@ -80,6 +80,8 @@ _SIGNATURES = {
     "vfi_bm25_set_profile": (C.c_int, [_P, C.c_int]),
     "vfi_bm25_get_stats": (C.c_int, [_P, C.POINTER(Bm25Stats), C.c_int]),
     "vfi_fuse_rrf": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
+    "vfi_index_search_begin": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P, _P, C.POINTER(C.c_int)]),
+    "vfi_index_search_finish": (C.c_int, [_P, C.c_int]),
     "vfi_stem_english": (C.c_int, [C.c_char_p, _P, C.c_int64, _P, C.c_int64, _P]),
     "vfi_tokenize_ascii": (C.c_int, [C.c_char_p, C.c_int64, _P, _P, C.c_int64, _P]),
     "vfi_fuse_union": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P]),

@@ -212,6 +212,22 @@ constexpr int kGemvMaxKeep = 512;
 
 }  // namespace
 
+// One batch between vfi_index_search_begin and vfi_index_search_finish (the synchronous search uses a slot too).
+constexpr int kSearchSlots = 4;
+struct SearchSlot {
+  bool busy = false;         // launched, not finished yet
+  bool needs_check = false;  // a certificate flag is on its way to h_flag[slot]
+  bool used_tau = false;     // the admission hint was on (a failed certificate is first retried without it)
+  const float* q = nullptr;
+  int nq = 0, k = 0;
+  float* out_scores = nullptr;
+  int64_t* out_ids = nullptr;
+  cudaStream_t st = nullptr;
+  cudaEvent_t done = nullptr;   // recorded behind the flag copy
+  cudaEvent_t pev[4] = {nullptr, nullptr, nullptr, nullptr};   // VFI_OPT_PROFILE: around the dominant kernel [0,1] and the tail [2,3]
+  uint64_t seq = 0;             // launch number (see vfi_index::prep_owner)
+};
+
 // =============================================================================================
 struct vfi_index {
   int d = 0, dp = 0, store = VFI_STORE_BF16, device = 0;
@@ -228,8 +244,11 @@ struct vfi_index {
   // workspace
   DevBuf w_qin, w_qcanon, w_qg, w_eps, w_cand, w_cand_count, w_keys, w_keys_n, w_bound, w_keys2, w_flag,
       w_out_scores, w_out_ids, w_stage, w_dbg, w_sel, w_tau;
-  int* h_flag = nullptr;   // pinned: [0] = n_flagged, [1..] = flagged query ids
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  int* h_flag = nullptr;   // pinned: [slot] = number of queries of that batch whose certificate failed
+  SearchSlot slots[kSearchSlots];
+  uint64_t launch_seq = 0;
+  uint64_t prep_owner = 0;   // seq of the batch whose prepared queries (w_qcanon, w_qg, w_eps) are in the workspace
+  int cur_slot = 0;        // slot of the batch being launched / finished (under mu)
   vfi_search_stats stats{};
   uint32_t* d_max_err = nullptr;
   std::mutex mu;
@@ -273,10 +292,10 @@ int vfi_index_create(int d, int store_dtype, int device, vfi_index_t** out) {
   idx->d_max_err = idx->xnorm_bits + 1;
   if (cudaMallocHost(&idx->h_flag, sizeof(int) * (kMaxQueriesPerLaunch + 1)) != cudaSuccess)
     return bail(fail(VFI_ERR_NOMEM, "cudaMallocHost failed"));
-  cudaEventCreate(&idx->ev0);
-  cudaEventCreate(&idx->ev1);
-  cudaEventCreate(&idx->ev2);
-  cudaEventCreate(&idx->ev3);
+  for (SearchSlot& sl : idx->slots) {
+    cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+    for (cudaEvent_t& e : sl.pev) cudaEventCreate(&e);
+  }
   cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kDenseSmemBytes);
   cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kDenseSmemBytes);
   cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_TOPK>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
@@ -308,10 +327,11 @@ int vfi_index_destroy(vfi_index_t* idx) {
   if (idx->master) cudaFree(idx->master);
   if (idx->xnorm_bits) cudaFree(idx->xnorm_bits);
   if (idx->h_flag) cudaFreeHost(idx->h_flag);
-  if (idx->ev0) cudaEventDestroy(idx->ev0);
-  if (idx->ev1) cudaEventDestroy(idx->ev1);
-  if (idx->ev2) cudaEventDestroy(idx->ev2);
-  if (idx->ev3) cudaEventDestroy(idx->ev3);
+  for (SearchSlot& sl : idx->slots) {
+    if (sl.done) cudaEventDestroy(sl.done);
+    for (cudaEvent_t e : sl.pev)
+      if (e) cudaEventDestroy(e);
+  }
   for (DevBuf* b : {&idx->w_qin, &idx->w_qcanon, &idx->w_qg, &idx->w_eps, &idx->w_cand, &idx->w_cand_count, &idx->w_keys,
                     &idx->w_keys_n, &idx->w_bound, &idx->w_keys2, &idx->w_flag, &idx->w_out_scores, &idx->w_out_ids,
                     &idx->w_stage, &idx->w_dbg, &idx->w_sel, &idx->w_tau})
@@ -618,7 +638,7 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
     p.cand_count = idx->w_cand_count.as<uint32_t>();
   }
   const bool prof = idx->opt_profile != 0 && profile;
-  if (prof) cudaEventRecord(idx->ev0, st);
+  if (prof) cudaEventRecord(idx->slots[idx->cur_slot].pev[0], st);
   const int grid = pair ? 2 * n_groups : n_groups * n_mtiles;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
@@ -640,7 +660,7 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
     else VFI_CUDA(cudaLaunchKernelEx(&cfg, vfi::dense_fused_kernel<vfi::MODE_STORE>, tq, td, p));
   }
   LAUNCHED();
-  if (prof) cudaEventRecord(idx->ev1, st);
+  if (prof) cudaEventRecord(idx->slots[idx->cur_slot].pev[1], st);
   VFI_CUDA(cudaGetLastError());
   if (profile) idx->stats.fused_launches++;
   if (o_groups) *o_groups = n_bufs;
@@ -649,10 +669,24 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
   return VFI_OK;
 }
 
-// one batch of <= kMaxQueriesPerLaunch queries already on the device; results to device buffers
-int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t st,
-                 bool no_hint = false) {
+// Enqueue one batch of <= kMaxQueriesPerLaunch queries already on the device (results to device buffers) into `slot`
+// without waiting: everything up to the copy of the certificate flag.  search_finish() waits and repairs.
+int search_launch(vfi_index* idx, int slot_id, const float* q_dev, int nq, int k, float* out_scores, int64_t* out_ids,
+                  cudaStream_t st, bool no_hint) {
+  SearchSlot& sl = idx->slots[slot_id];
+  sl.busy = true;
+  sl.needs_check = false;
+  sl.used_tau = false;
+  sl.q = q_dev;
+  sl.nq = nq;
+  sl.k = k;
+  sl.out_scores = out_scores;
+  sl.out_ids = out_ids;
+  sl.st = st;
+  sl.seq = ++idx->launch_seq;
+  idx->cur_slot = slot_id;
   VFI_TRY(prep_queries(idx, q_dev, nq, st));
+  idx->prep_owner = sl.seq;
   const int64_t n = idx->n;
   int keep = idx->opt_overfetch > 0 ? static_cast<int>(idx->opt_overfetch)
                                     : static_cast<int>(round_up(k + std::max(16, k / 4), 32));
@@ -668,7 +702,11 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
   if (path == 3 && (nq > vfi::kGemvMaxQ || keep > kGemvMaxKeep || n == 0 || !gemv_ok(idx))) path = (keep <= kFusedMaxKeep && n > 0) ? 2 : 1;
   idx->stats.last_path = path;
   idx->stats.last_overfetch = keep;
-  if (path == 1) return exhaustive_pass(idx, nullptr, nq, k, out_scores, out_ids, st);
+  if (path == 1) {      // every row scored canonically: nothing to certify
+    VFI_TRY(exhaustive_pass(idx, nullptr, nq, k, out_scores, out_ids, st));
+    VFI_CUDA(cudaEventRecord(sl.done, st));
+    return VFI_OK;
+  }
 
   int n_groups = 0, nq_pad = 0, cap = 0;
   const float* tau = nullptr;
@@ -711,7 +749,7 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
     VFI_TRY(idx->w_cand.ensure(static_cast<size_t>(n_groups) * nq_pad * cap * 8));
     VFI_TRY(idx->w_cand_count.ensure(static_cast<size_t>(n_groups) * nq_pad * 4));
     const bool prof = idx->opt_profile != 0;
-    if (prof) cudaEventRecord(idx->ev0, st);
+    if (prof) cudaEventRecord(idx->slots[idx->cur_slot].pev[0], st);
     if (idx->store == VFI_STORE_F32)
       gemv_launch<float>(nq, n_groups, smem, st, idx->master, idx->dp, idx->dp, n, idx->w_qcanon.as<float>(), keep, cap_s,
                          idx->w_cand.as<uint64_t>(), idx->w_cand_count.as<uint32_t>(), nq_pad, cap);
@@ -719,15 +757,15 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
       gemv_launch<uint16_t>(nq, n_groups, smem, st, idx->g, idx->kp, idx->dp, n, idx->w_qcanon.as<float>(), keep, cap_s,
                             idx->w_cand.as<uint64_t>(), idx->w_cand_count.as<uint32_t>(), nq_pad, cap);
     LAUNCHED();
-    if (prof) cudaEventRecord(idx->ev1, st);
+    if (prof) cudaEventRecord(idx->slots[idx->cur_slot].pev[1], st);
     VFI_CUDA(cudaGetLastError());
     idx->stats.fused_launches++;
   }
-  VFI_TRY(idx->w_flag.ensure(static_cast<size_t>(kMaxQueriesPerLaunch + 1) * 4));
-  int* d_flag = idx->w_flag.as<int>();
+  VFI_TRY(idx->w_flag.ensure(static_cast<size_t>(kSearchSlots) * (kMaxQueriesPerLaunch + 1) * 4));
+  int* d_flag = idx->w_flag.as<int>() + static_cast<size_t>(slot_id) * (kMaxQueriesPerLaunch + 1);   // [0] count, [1..] flagged queries
   VFI_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
   const bool tail_prof = idx->opt_profile != 0;
-  if (tail_prof) cudaEventRecord(idx->ev2, st);
+  if (tail_prof) cudaEventRecord(idx->slots[idx->cur_slot].pev[2], st);
   if (keep <= 256 && idx->dp <= vfi::kRfMaxDp && idx->opt_tail != 1) {
     // K1c: per-query union of the group buffers -> k' best by tensor-core score; then K2: one thread per candidate
     // rescoring + final order + certificate
@@ -804,35 +842,73 @@ int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_s
     LAUNCHED();
     VFI_CUDA(cudaGetLastError());
   }
-  if (tail_prof) cudaEventRecord(idx->ev3, st);
-  VFI_CUDA(cudaMemcpyAsync(idx->h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
-  VFI_CUDA(cudaStreamSynchronize(st));
-  if (idx->opt_profile) {
+  if (tail_prof) cudaEventRecord(idx->slots[idx->cur_slot].pev[3], st);
+  VFI_CUDA(cudaMemcpyAsync(idx->h_flag + slot_id, d_flag, 4, cudaMemcpyDeviceToHost, st));
+  VFI_CUDA(cudaEventRecord(sl.done, st));
+  sl.needs_check = true;
+  sl.used_tau = tau != nullptr;
+  return VFI_OK;
+}
+
+// Wait for the batch in `slot`, read its certificate flag and repair what failed: a batch pruned too hard by the admission
+// hint is redone without it, queries whose candidates tie across the cut are re-run by the exhaustive canonical pass.
+int search_finish(vfi_index* idx, int slot_id) {
+  SearchSlot& sl = idx->slots[slot_id];
+  if (!sl.busy) return fail(VFI_ERR_INVALID, "no batch in flight for this ticket");
+  sl.busy = false;
+  VFI_CUDA(cudaEventSynchronize(sl.done));
+  idx->cur_slot = slot_id;
+  if (idx->opt_profile && sl.needs_check) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, idx->ev2, idx->ev3) == cudaSuccess) {
+    if (cudaEventElapsedTime(&ms, idx->slots[idx->cur_slot].pev[2], idx->slots[idx->cur_slot].pev[3]) == cudaSuccess) {
       idx->stats.tail_ms_total += ms;
       idx->stats.tail_ms_samples++;
     } else {
       cudaGetLastError();
     }
-    if (cudaEventElapsedTime(&ms, idx->ev0, idx->ev1) == cudaSuccess) {
+    if (cudaEventElapsedTime(&ms, idx->slots[idx->cur_slot].pev[0], idx->slots[idx->cur_slot].pev[1]) == cudaSuccess) {
       idx->stats.fused_ms_total += ms;
       idx->stats.fused_ms_samples++;
     } else {
       cudaGetLastError();
     }
   }
-  const int n_flagged = idx->h_flag[0];
-  if (n_flagged > 0 && tau != nullptr && idx->opt_tau_hint == 1) {
+  if (!sl.needs_check) return VFI_OK;
+  const int n_flagged = idx->h_flag[slot_id];
+  if (n_flagged <= 0) return VFI_OK;
+  if (sl.used_tau && idx->opt_tau_hint == 1) {
     // the hint pruned too much for some query: redo the batch without it (same kernels, no pruning)
     idx->stats.hint_retries++;
-    return search_batch(idx, q_dev, nq, k, out_scores, out_ids, st, true);
+    VFI_TRY(search_launch(idx, slot_id, sl.q, sl.nq, sl.k, sl.out_scores, sl.out_ids, sl.st, true));
+    return search_finish(idx, slot_id);
   }
-  if (n_flagged > 0) {
-    idx->stats.retried_queries += n_flagged;
-    VFI_TRY(exhaustive_pass(idx, d_flag + 1, n_flagged, k, out_scores, out_ids, st));
+  idx->stats.retried_queries += n_flagged;
+  if (idx->prep_owner != sl.seq) {   // a later batch (or the repair of another one) has replaced the prepared queries
+    VFI_TRY(prep_queries(idx, sl.q, sl.nq, sl.st));
+    idx->prep_owner = sl.seq;
   }
+  const int* flagged = idx->w_flag.as<int>() + static_cast<size_t>(slot_id) * (kMaxQueriesPerLaunch + 1) + 1;
+  VFI_TRY(exhaustive_pass(idx, flagged, n_flagged, sl.k, sl.out_scores, sl.out_ids, sl.st));
+  VFI_CUDA(cudaStreamSynchronize(sl.st));
   return VFI_OK;
+}
+
+int free_slot(const vfi_index* idx) {
+  for (int i = 0; i < kSearchSlots; ++i)
+    if (!idx->slots[i].busy) return i;
+  return -1;
+}
+
+// the synchronous form: launch + finish
+int search_batch(vfi_index* idx, const float* q_dev, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+  const int slot = free_slot(idx);
+  if (slot < 0) return fail(VFI_ERR_UNSUPPORTED, "too many batches in flight: finish a ticket of vfi_index_search_begin first");
+  const int rc = search_launch(idx, slot, q_dev, nq, k, out_scores, out_ids, st, false);
+  if (rc != VFI_OK) {
+    idx->slots[slot].busy = false;
+    return rc;
+  }
+  return search_finish(idx, slot);
 }
 
 }  // namespace
@@ -873,6 +949,36 @@ int vfi_index_search(vfi_index_t* idx, const float* q, int64_t nq, int k, float*
     }
   }
   return VFI_OK;
+}
+
+int vfi_index_search_begin(vfi_index_t* idx, const float* q, int64_t nq, int k, float* out_scores, int64_t* out_ids, void* stream,
+                           int* ticket) {
+  if (!idx || !ticket || !q || !out_scores || !out_ids || nq <= 0) return fail(VFI_ERR_INVALID, "bad argument to vfi_index_search_begin");
+  if (k <= 0) return fail(VFI_ERR_INVALID, "k must be positive");
+  if (k > VFI_MAX_K) return fail(VFI_ERR_UNSUPPORTED, "k exceeds VFI_MAX_K (2048)");
+  if (nq > kMaxQueriesPerLaunch) return fail(VFI_ERR_UNSUPPORTED, "vfi_index_search_begin takes at most 1024 queries per batch");
+  std::lock_guard<std::mutex> lock(idx->mu);
+  DeviceGuard guard(idx->device);
+  if (!guard.ok) return fail(VFI_ERR_CUDA, "cudaSetDevice failed");
+  const int slot = free_slot(idx);
+  if (slot < 0) return fail(VFI_ERR_UNSUPPORTED, "too many batches in flight (4): finish a ticket first");
+  idx->stats.searches++;
+  idx->stats.queries += nq;
+  const int rc = search_launch(idx, slot, q, static_cast<int>(nq), k, out_scores, out_ids, static_cast<cudaStream_t>(stream), false);
+  if (rc != VFI_OK) {
+    idx->slots[slot].busy = false;
+    return rc;
+  }
+  *ticket = slot;
+  return VFI_OK;
+}
+
+int vfi_index_search_finish(vfi_index_t* idx, int ticket) {
+  if (!idx || ticket < 0 || ticket >= kSearchSlots) return fail(VFI_ERR_INVALID, "bad ticket");
+  std::lock_guard<std::mutex> lock(idx->mu);
+  DeviceGuard guard(idx->device);
+  if (!guard.ok) return fail(VFI_ERR_CUDA, "cudaSetDevice failed");
+  return search_finish(idx, ticket);
 }
 
 int vfi_index_read_rows(vfi_index_t* idx, int64_t first, int64_t n, float* out, int mem, void* stream) {

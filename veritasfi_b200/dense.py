@@ -19,6 +19,14 @@ def _stream_ptr(device: torch.device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class SearchTicket:
+    """One batch in flight: keeps the query and result tensors alive until `DenseIndex.search_finish`."""
+    __slots__ = ("ticket", "q", "ids", "scores")
+
+    def __init__(self, ticket: int, q: torch.Tensor, ids: torch.Tensor, scores: torch.Tensor):
+        self.ticket, self.q, self.ids, self.scores = ticket, q, ids, scores
+
+
 class DenseIndex:
     """Flat inner-product index over a corpus shard resident in HBM.
 
@@ -89,6 +97,26 @@ class DenseIndex:
                                               C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()),
                                               N.MEM_DEVICE, _stream_ptr(self.device)))
         return ids, scores
+
+    def search_begin(self, q: torch.Tensor, k: int) -> "SearchTicket":
+        """Enqueue one batch (B <= 1024) and return at once; `search_finish(ticket)` waits, certifies and hands out
+        (ids, scores).  Beginning batch i+1 before finishing batch i keeps the GPU busy while the host looks at the
+        certificate flag of batch i (vfi_index_search_begin / vfi_index_search_finish)."""
+        if not (isinstance(q, torch.Tensor) and q.is_cuda and q.dtype == torch.float32 and q.dim() == 2
+                and q.shape[1] == self.d and q.shape[0] > 0):
+            raise ValueError("search_begin: need a non-empty float32 [B, d] cuda tensor")
+        q = q.contiguous()
+        B = q.shape[0]
+        ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
+        scores = torch.empty((B, k), dtype=torch.float32, device=self.device)
+        t = C.c_int(-1)
+        N.check(N.load().vfi_index_search_begin(self._h, C.c_void_p(q.data_ptr()), B, int(k), C.c_void_p(scores.data_ptr()),
+                                                C.c_void_p(ids.data_ptr()), _stream_ptr(self.device), C.byref(t)))
+        return SearchTicket(t.value, q, ids, scores)
+
+    def search_finish(self, ticket: "SearchTicket"):
+        N.check(N.load().vfi_index_search_finish(self._h, ticket.ticket))
+        return ticket.ids, ticket.scores
 
     def search_host(self, q: np.ndarray, k: int):
         """Host in, host out (pinned or pageable numpy): the reference-facing call, copies included."""
