@@ -187,6 +187,12 @@ def main():
         print(json.dumps(line))
         return
 
+    # stdout carries exactly ONE line, the JSON result: anything a library writes to file descriptor 1 meanwhile (NCCL prints
+    # its version banner there) is sent to stderr instead
+    sys.stdout.flush()
+    result_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -200,7 +206,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL logs its version there)
         dist.init_process_group("nccl", device_id=dev)
 
     lo, hi = shard_bounds(w["n"], world, rank)
@@ -359,7 +364,7 @@ def main():
             line["cpu_baseline"] = cpu
         elif world > 1:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        print(json.dumps(line), file=result_out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
