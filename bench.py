@@ -146,8 +146,8 @@ def cpu_reference_arm(w, steps: int, warmup: int, rows_sample: int, threads: int
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)   # ~1.7 s at C3: long enough for the power-cap governor to settle
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--cpu-rows", type=int, default=250_000, help="rows of the CPU baseline sample")
@@ -319,7 +319,9 @@ def main():
     launches = N.launch_count() - launches0
     st = index.stats()
     clocks = sampler.stop() if rank == 0 else None
+    index.stats(reset=True)
     ms_e2e = timed(step_e2e, steps)
+    st_e2e = index.stats()
     ids, scores = step_device()
     torch.cuda.synchronize()
 
@@ -354,7 +356,9 @@ def main():
                 "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic", "config": config, "roofline": roofline, "clocks": clocks,
                 "e2e": {"value": w["b"] / (ms_e2e / steps * 1e-3), "unit": "queries/s", "ms_per_step": ms_e2e / steps,
-                        "h2d_bytes_per_step": w["b"] * w["d"] * 4, "d2h_bytes_per_step": w["b"] * w["k"] * 12},
+                        "h2d_bytes_per_step": w["b"] * w["d"] * 4, "d2h_bytes_per_step": w["b"] * w["k"] * 12,
+                        "kernel_ms": st_e2e.fused_ms_total / max(1, st_e2e.fused_ms_samples),
+                        "tail_ms": st_e2e.tail_ms_total / max(1, st_e2e.tail_ms_samples)},
                 "gpu_launches": int(launches),
                 "search": {"path": int(st.last_path), "overfetch": int(st.last_overfetch), "retried_queries": int(st.retried_queries),
                            "hint_retries": int(st.hint_retries), "max_abs_tc_err": float(st.max_abs_err),
