@@ -113,7 +113,8 @@ enum {
   VFI_OPT_OVERFETCH = 1,     /* candidates kept per query by the tensor-core pass (0 = auto) */
   VFI_OPT_FORCE_PATH = 2,    /* 0 auto, 1 exhaustive exact, 2 fused tcgen05, 3 streaming GEMV */
   VFI_OPT_PROFILE = 3,       /* 1: bracket the dominant kernel with CUDA events */
-  VFI_OPT_TAU_HINT = 4,      /* 1 (default): estimate a per-query admission threshold from a row sample; 0: off (2: debug, admit nothing) */
+  VFI_OPT_TAU_HINT = 4,      /* 1 (default): estimate a per-query admission threshold from a row sample (chunk maxima); 0: off;
+                                2: debug, admit nothing; 3: as 1 from every sampled score */
   VFI_OPT_NUM_CTAS = 5,      /* 0 = one CTA per SM */
   VFI_OPT_CLUSTER = 6,       /* single-CTA kernel only: CTAs per cluster sharing corpus tiles by TMA multicast: 0/1 off, 2, 4, 8 */
   VFI_OPT_CTA_PAIR = 7,      /* tcgen05 cta_group::2 kernel (two SMs share every corpus tile): 0 auto (on when the batch has an

@@ -141,9 +141,13 @@ def test_admission_hint_does_not_change_results(torch_cuda):
     idx.set_option(N.OPT_FORCE_PATH, N.PATH_FUSED)
     idx.set_option(N.OPT_TAU_HINT, 0)
     i0, s0 = idx.search_batch(q, 20)
-    idx.set_option(N.OPT_TAU_HINT, 1)            # the library default
+    idx.set_option(N.OPT_TAU_HINT, 1)            # the library default: threshold from the chunk maxima of a row sample
     i1, s1 = idx.search_batch(q, 20)
     assert torch.equal(i0, i1) and torch.equal(s0, s1)
+    assert idx.stats().hint_retries == 0
+    idx.set_option(N.OPT_TAU_HINT, 3)            # threshold from every sampled score
+    i3, s3 = idx.search_batch(q, 20)
+    assert torch.equal(i0, i3) and torch.equal(s0, s3)
     D0, I0 = flat_ip.search(xq, xb, 20)
     assert (i1.cpu().numpy() == I0).all() and (s1.cpu().numpy() == D0).all()
     idx.close()

@@ -39,7 +39,7 @@ constexpr int kTmemCols = 512;
 constexpr int kDenseSmemBytes =
     1024 /*align slack*/ + kStages * (kABytes + kBBytes) + 256 /*barriers*/ + 8 * 256 * 4 /*hist*/;
 
-enum { MODE_TOPK = 0, MODE_STORE = 1 };
+enum { MODE_TOPK = 0, MODE_STORE = 1, MODE_CHUNKMAX = 2 };   // CHUNKMAX: one value per (query, 32-row chunk), its largest score
 
 struct DenseParams {
   int nq;                 // queries in this launch
@@ -54,7 +54,7 @@ struct DenseParams {
   uint64_t* cand;         // [2*n_groups][nq_pad][cap]   (one buffer per epilogue set)
   uint32_t* cand_count;   // [2*n_groups][nq_pad]
   const float* tau_init;  // [nq] admission hints (rows with score <= hint are ignored) or nullptr
-  float* scores_out;      // MODE_STORE: [nq_pad][ld_scores]
+  float* scores_out;      // MODE_STORE: [nq_pad][ld_scores] scores; MODE_CHUNKMAX: [nq_pad][ld_scores] chunk maxima (ld = 8 per tile)
   int64_t ld_scores;
   int cluster;            // CTAs per cluster (1, 2, 4 or 8; divides n_mtiles): they share each corpus tile by TMA multicast
 };
@@ -103,6 +103,20 @@ __device__ __forceinline__ void admit_chunk(const float (&v)[32], uint32_t id0, 
     }
     __syncwarp();
   }
+}
+
+// largest of the 32 scores of a chunk, rows at or beyond n_rows excluded (TMA fills them with zeros)
+__device__ __forceinline__ float chunk_max(const float (&v)[32], uint32_t row_base, uint32_t n_rows) {
+  float mx = -INFINITY;
+  if (row_base + 32 <= n_rows) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (row_base + j < n_rows) mx = fmaxf(mx, v[j]);
+  }
+  return mx;
 }
 
 // ===================== epilogue: TMEM -> registers -> threshold filter =====================
@@ -155,6 +169,9 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t tm
           for (int j = 0; j < 8; ++j)
             dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
+      } else if (MODE == MODE_CHUNKMAX) {
+        const float mx = chunk_max(v, row0 + c * 32, static_cast<uint32_t>(p.n_rows));
+        if (valid_q) p.scores_out[static_cast<size_t>(qi) * p.ld_scores + (row0 >> 5) + c] = mx;
       } else {
         admit_chunk(v, row0 + c * 32, static_cast<uint32_t>(p.n_rows), valid_q, tau_f, tau_key, count, buf, p.cap, p.keep,
                     my_hist, lane);
@@ -475,6 +492,9 @@ dense_fused_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
               for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
+          } else if (MODE == MODE_CHUNKMAX) {
+            const float mx = chunk_max(v, row0 + c * 32, static_cast<uint32_t>(p.n_rows));
+            if (valid_q) p.scores_out[static_cast<size_t>(qi) * p.ld_scores + (row0 >> 5) + c] = mx;
           } else {
             admit_chunk(v, row0 + c * 32, static_cast<uint32_t>(p.n_rows), valid_q, tau_f, tau_key, count, buf, p.cap, p.keep,
                         my_hist, lane);

@@ -298,9 +298,11 @@ int vfi_index_create(int d, int store_dtype, int device, vfi_index_t** out) {
   }
   cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kDenseSmemBytes);
   cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kDenseSmemBytes);
+  cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_CHUNKMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kDenseSmemBytes);
   cudaFuncSetAttribute(vfi::dense_fused_kernel<vfi::MODE_TOPK>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
   cudaFuncSetAttribute(vfi::dense_fused_pair_kernel<vfi::MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kPairSmemBytes);
   cudaFuncSetAttribute(vfi::dense_fused_pair_kernel<vfi::MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kPairSmemBytes);
+  cudaFuncSetAttribute(vfi::dense_fused_pair_kernel<vfi::MODE_CHUNKMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kPairSmemBytes);
   gemv_set_smem_attr();
   cudaFuncSetAttribute(vfi::select_rescore_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(vfi::TailSmem)));
   cudaFuncSetAttribute(vfi::select_rescore_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(vfi::TailSmem)));
@@ -654,9 +656,11 @@ int launch_fused(vfi_index* idx, int nq, int keep, int mode, float* scores_out, 
   cfg.numAttrs = 1;
   if (pair) {
     if (mode == vfi::MODE_TOPK) VFI_CUDA(cudaLaunchKernelEx(&cfg, vfi::dense_fused_pair_kernel<vfi::MODE_TOPK>, tq, td, p));
+    else if (mode == vfi::MODE_CHUNKMAX) VFI_CUDA(cudaLaunchKernelEx(&cfg, vfi::dense_fused_pair_kernel<vfi::MODE_CHUNKMAX>, tq, td, p));
     else VFI_CUDA(cudaLaunchKernelEx(&cfg, vfi::dense_fused_pair_kernel<vfi::MODE_STORE>, tq, td, p));
   } else {
     if (mode == vfi::MODE_TOPK) VFI_CUDA(cudaLaunchKernelEx(&cfg, vfi::dense_fused_kernel<vfi::MODE_TOPK>, tq, td, p));
+    else if (mode == vfi::MODE_CHUNKMAX) VFI_CUDA(cudaLaunchKernelEx(&cfg, vfi::dense_fused_kernel<vfi::MODE_CHUNKMAX>, tq, td, p));
     else VFI_CUDA(cudaLaunchKernelEx(&cfg, vfi::dense_fused_kernel<vfi::MODE_STORE>, tq, td, p));
   }
   LAUNCHED();
@@ -720,13 +724,19 @@ int search_launch(vfi_index* idx, int slot_id, const float* q_dev, int nq, int k
     const int64_t rs = 2 * static_cast<int64_t>(keep) + 1;
     const int64_t rr = n / rs;
     if (rr >= 4 * m || idx->opt_tau_hint == 2) {
-      const int64_t ld = ceil_div(rr, vfi::kBN) * vfi::kBN;
+      // The sample pass keeps one value per (query, 32 sampled rows) — the chunk's largest tensor-core score — instead of
+      // every score: the m-th largest chunk maximum is at most the m-th largest sampled score (equal unless two of the
+      // best m samples share a chunk), so it is a valid, marginally looser hint, and the threshold kernel reads 32 x less.
+      // VFI_OPT_TAU_HINT = 3 keeps the full sample (every score stored) for comparison.
+      const bool full = idx->opt_tau_hint == 3;
+      const int64_t ld = full ? ceil_div(rr, vfi::kBN) * vfi::kBN : ceil_div(rr, vfi::kBN) * (vfi::kBN / 32);
+      const int64_t n_vals = full ? rr : ceil_div(rr, 32);
       const int64_t nq_pad_s = ceil_div(nq, vfi::kBM) * vfi::kBM;
       VFI_TRY(idx->w_dbg.ensure(static_cast<size_t>(nq_pad_s) * ld * 4));
       VFI_TRY(idx->w_tau.ensure(static_cast<size_t>(nq) * 4));
-      VFI_TRY(launch_fused(idx, nq, 32, vfi::MODE_STORE, idx->w_dbg.as<float>(), ld, nullptr, nullptr, nullptr, nullptr, st, rr,
-                           rs, false));
-      vfi::tau_from_scores_kernel<<<nq, 256, sizeof(vfi::SelectSmem), st>>>(idx->w_dbg.as<float>(), ld, static_cast<int>(rr), m,
+      VFI_TRY(launch_fused(idx, nq, 32, full ? vfi::MODE_STORE : vfi::MODE_CHUNKMAX, idx->w_dbg.as<float>(), ld, nullptr, nullptr,
+                           nullptr, nullptr, st, rr, rs, false));
+      vfi::tau_from_scores_kernel<<<nq, 256, sizeof(vfi::SelectSmem), st>>>(idx->w_dbg.as<float>(), ld, static_cast<int>(n_vals), m,
                                                                            idx->w_tau.as<float>(), idx->opt_tau_hint == 2 ? 1 : 0);
       LAUNCHED();
       VFI_CUDA(cudaGetLastError());
@@ -876,7 +886,7 @@ int search_finish(vfi_index* idx, int slot_id) {
   if (!sl.needs_check) return VFI_OK;
   const int n_flagged = idx->h_flag[slot_id];
   if (n_flagged <= 0) return VFI_OK;
-  if (sl.used_tau && idx->opt_tau_hint == 1) {
+  if (sl.used_tau && (idx->opt_tau_hint == 1 || idx->opt_tau_hint == 3)) {
     // the hint pruned too much for some query: redo the batch without it (same kernels, no pruning)
     idx->stats.hint_retries++;
     VFI_TRY(search_launch(idx, slot_id, sl.q, sl.nq, sl.k, sl.out_scores, sl.out_ids, sl.st, true));
