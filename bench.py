@@ -153,7 +153,6 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=250_000, help="rows of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hint", type=int, default=1)
-    ap.add_argument("--tail", type=int, default=0, help="VFI_OPT_TAIL (0 default: selection kernel + bulk-copy rescoring kernel, 1 single-launch tail, 2/3 variants)")
     ap.add_argument("--sync", action="store_true",
                     help="N=1: one synchronous search per step instead of two batches in flight (search_begin/search_finish)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
@@ -219,7 +218,6 @@ def main():
     torch.cuda.synchronize()
     index.set_option(N.OPT_TAU_HINT, args.hint)
     index.set_option(N.OPT_PROFILE, 1)
-    index.set_option(N.OPT_TAIL, args.tail)
     searcher = make_sharded_dense(index, exchange=args.exchange, max_nq=w["b"], max_k=w["k"])
     q_dev = synth.dense_queries_torch(w["b"], w["d"], SEED, dev)
     q_pin = torch.empty((w["b"], w["d"]), dtype=torch.float32).pin_memory()

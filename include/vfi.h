@@ -9,6 +9,8 @@
  *   vfi_bm25_*       replaces bm25s.BM25.load(...) / .retrieve(tokens, k)   src/utils/bm25Retriever.py:46,75-79
  *   vfi_fuse_union   replaces the shared seen_ids ordered de-dup union      src/utils/ensembleRetriever.py:58,72-74,148-150,194-196
  *   vfi_fuse_rrf     reciprocal-rank fusion (north_star; not in the reference, SURVEY.md finding 4)
+ *   vfi_fuse_hybrid  the fusion step of the sharded hybrid retriever in one launch: title -> chunk mapping, per-path
+ *                    de-duplication, dropping of BM25's zero-score filler, RRF (north_star configs[3])
  *   vfi_merge_topk   global top-k after the all-gather of per-shard results (no reference counterpart;
  *                    the reference only replicates workers, experiments/retriever/step3_mul.py:405-446)
  *   vfi_cosine_topk  replaces cosine_similarity + argsort top-k             experiments/retriever/step3_mul.py:255-289,
@@ -99,36 +101,43 @@ int vfi_index_pairwise(vfi_index_t* idx, const int64_t* ids, int n, float* out, 
 int vfi_index_search(vfi_index_t* idx, const float* q, int64_t nq, int k, float* out_scores,
                      int64_t* out_ids, int mem, void* stream);
 
-/* Pipelined form for device buffers: begin() enqueues one batch (nq <= 1024) on `stream` and returns at once with a
+/* Threading: vfi_index_search, vfi_index_search_begin/finish, vfi_index_pairwise, vfi_index_read_rows and
+ * vfi_index_reconstruct may be called from any number of threads on one index at the same time (the reference calls
+ * retriever.invoke from concurrent request threads without a lock, src/utils/vllmChatService.py:85-88,404): every call
+ * works in a workspace of its own taken from a pool, and a host-buffer search that passes no stream runs on a stream of
+ * its own.  add / reserve / set_option / set_id_offset / destroy must not run concurrently with a search (as with faiss).
+ *
+ * Pipelined form for device buffers: begin() enqueues one batch (nq <= 1024) on `stream` and returns at once with a
  * ticket; finish(ticket) waits for that batch, checks its exactness certificate and repairs the rare query that failed it,
- * after which out_scores / out_ids hold the same bits vfi_index_search would have produced.  Up to 4 batches may be in
- * flight per index, all on the same stream; q and the output buffers must stay valid until finish.  A serving loop that
- * begins batch i+1 before finishing batch i never leaves the GPU idle during the host's look at the certificate flag. */
+ * after which out_scores / out_ids hold the same bits vfi_index_search would have produced.  Up to 64 batches may be in
+ * flight per index; q and the output buffers must stay valid until finish.  A serving loop that begins batch i+1
+ * before finishing batch i never leaves the GPU idle during the host's look at the certificate flag. */
 int vfi_index_search_begin(vfi_index_t* idx, const float* q, int64_t nq, int k, float* out_scores,
                            int64_t* out_ids, void* stream, int* ticket);
 int vfi_index_search_finish(vfi_index_t* idx, int ticket);
+/* device address of the batch's certificate counter (> 0 once its kernels ran = some query still needs the repair of
+ * finish()); valid until finish(ticket).  Lets a kernel enqueued behind the batch (vfi_exchange_merge_flagged) tell its
+ * peers that the rows it is about to send are not final. */
+int vfi_index_ticket_flag(vfi_index_t* idx, int ticket, const int** device_flag);
 
 /* tuning / introspection ------------------------------------------------------------------ */
 enum {
   VFI_OPT_OVERFETCH = 1,     /* candidates kept per query by the tensor-core pass (0 = auto) */
-  VFI_OPT_FORCE_PATH = 2,    /* 0 auto, 1 exhaustive exact, 2 fused tcgen05, 3 streaming GEMV */
+  VFI_OPT_FORCE_PATH = 2,    /* 0 auto, 1 exact streaming scorer (every row scored canonically; deep k for few queries, tiny
+                                shards, repairs), 2 fused tcgen05 GEMM + top-k', 3 streaming GEMV (few queries, k' <= 512) */
   VFI_OPT_PROFILE = 3,       /* 1: bracket the dominant kernel with CUDA events */
   VFI_OPT_TAU_HINT = 4,      /* 1 (default): estimate a per-query admission threshold from a row sample (chunk maxima); 0: off;
                                 2: debug, admit nothing; 3: as 1 from every sampled score */
   VFI_OPT_NUM_CTAS = 5,      /* 0 = one CTA per SM */
-  VFI_OPT_CLUSTER = 6,       /* single-CTA kernel only: CTAs per cluster sharing corpus tiles by TMA multicast: 0/1 off, 2, 4, 8 */
-  VFI_OPT_CTA_PAIR = 7,      /* tcgen05 cta_group::2 kernel (two SMs share every corpus tile): 0 auto (on when the batch has an
-                                even number of 128-query tiles), 1 off, 2 on */
-  VFI_OPT_TAIL = 8           /* tail after the tensor-core pass for k' <= 256: 0 auto (selection kernel, then a thread-per-candidate
-                                rescoring kernel fed by 256-byte bulk copies), 1 the single-launch select+rescore kernel,
-                                2 as 0 with 128-byte pieces (1024 queries in one wave), 3 as 0 with a two-stage ring */
+  VFI_OPT_CTA_PAIR = 7       /* tcgen05 cta_group::2 kernel (two SMs share every corpus tile; a batch with an odd number of
+                                128-query tiles gets a padding tile): 0 auto = on, 1 off (single-CTA kernel), 2 on */
 };
 int vfi_index_set_option(vfi_index_t* idx, int opt, int64_t value);
 
 typedef struct vfi_search_stats {
   int64_t searches;            /* search calls */
   int64_t queries;             /* queries processed */
-  int64_t retried_queries;     /* queries whose certificate failed and were re-run exhaustively */
+  int64_t retried_queries;     /* queries whose certificate failed and were re-run by the exact streaming scorer */
   int64_t fused_launches;      /* launches of the tcgen05 kernel */
   double fused_ms_total;       /* summed device time of those launches (VFI_OPT_PROFILE=1) */
   int64_t fused_ms_samples;    /* launches that contributed to fused_ms_total */
@@ -180,6 +189,13 @@ int vfi_exchange_connect(vfi_exchange_t* ex, const void* handles /* world x VFI_
 int vfi_exchange_set_timeout_ms(vfi_exchange_t* ex, int64_t ms);
 int vfi_exchange_merge(vfi_exchange_t* ex, const float* scores, const int64_t* ids, int64_t nq, int k, int k_out,
                        float* out_scores, int64_t* out_ids, void* stream);
+/* The same with the batch's state attached: fail_a / fail_b (device ints, either may be NULL; see vfi_index_ticket_flag) say
+ * whether this rank's rows may still be repaired; *any_fail (device int, may be NULL; zero it before the call) is set to 1
+ * on EVERY rank when any rank said so — the ranks then agree, without a host collective, to exchange the batch again
+ * after their repairs. */
+int vfi_exchange_merge_flagged(vfi_exchange_t* ex, const float* scores, const int64_t* ids, int64_t nq, int k, int k_out,
+                               float* out_scores, int64_t* out_ids, const int* fail_a, const int* fail_b, int* any_fail,
+                               void* stream);
 int vfi_exchange_destroy(vfi_exchange_t* ex);
 
 /* ---- BM25 over token-major postings (bm25s CSC arrays) ----------------------------------- */
@@ -189,11 +205,17 @@ int vfi_exchange_destroy(vfi_exchange_t* ex);
 int vfi_bm25_create(const int64_t* indptr, const int32_t* indices, const float* data,
                     int64_t n_vocab, int64_t n_docs, int64_t id_offset, int device,
                     vfi_bm25_t** out);
+/* the same with `mem` saying where the three arrays live (VFI_MEM_DEVICE: postings built on the GPU are adopted by a
+ * device-to-device copy; validation runs on the device either way) */
+int vfi_bm25_create_from(const int64_t* indptr, const int32_t* indices, const float* data,
+                         int64_t n_vocab, int64_t n_docs, int64_t id_offset, int mem, int device,
+                         vfi_bm25_t** out);
 int vfi_bm25_destroy(vfi_bm25_t* b);
 int64_t vfi_bm25_ndocs(const vfi_bm25_t* b);
 /* q_tokens int32 [q_indptr[nq]] token ids in query order (unknown tokens already dropped,
- * repeats kept), q_indptr int64 [nq+1]: HOST arrays (they come from the host tokeniser). Scores accumulate
- * in fp32 in query-token order. `mem` says where out_scores / out_ids live (VFI_MEM_HOST or VFI_MEM_DEVICE). */
+ * repeats kept; any number of tokens per query), q_indptr int64 [nq+1]: HOST arrays (they come from the host
+ * tokeniser). Scores accumulate in fp32 in query-token order. k <= VFI_MAX_K. `mem` says where out_scores / out_ids
+ * live (VFI_MEM_HOST or VFI_MEM_DEVICE).  Thread-safe (per-call scratch from a pool). */
 int vfi_bm25_search(vfi_bm25_t* b, const int32_t* q_tokens, const int64_t* q_indptr, int64_t nq,
                     int k, float* out_scores, int64_t* out_ids, int mem, void* stream);
 /* all n_docs scores of one query (host/device fp32 [n_docs]); serves retrieve(k = N) */
@@ -203,6 +225,9 @@ int vfi_bm25_score_all(vfi_bm25_t* b, const int32_t* q_tokens, int64_t n_tokens,
  * order — bm25s retrieve(k = N) as called at ensembleRetriever.py:189. Host outputs. */
 int vfi_bm25_rank_all(vfi_bm25_t* b, const int32_t* q_tokens, int64_t n_tokens, float* out_scores,
                       int64_t* out_ids, void* stream);
+/* ranks [first, first+count) of that order only (the tail behind an eager top-k, produced when a caller asks for it) */
+int vfi_bm25_rank_range(vfi_bm25_t* b, const int32_t* q_tokens, int64_t n_tokens, int64_t first, int64_t count,
+                        float* out_scores, int64_t* out_ids, void* stream);
 typedef struct vfi_bm25_stats {
   int64_t launches;
   double score_ms_total;   /* device time of the scoring kernel (profile on) */
@@ -224,6 +249,19 @@ int vfi_fuse_rrf(const int64_t* ids, int64_t nq, int n_paths, int depth, float k
 int vfi_fuse_union(const int64_t* ids, const float* scores, int64_t nq, int n_paths, int depth,
                    int64_t* out_ids, float* out_scores, int32_t* out_path, int32_t* out_count,
                    int mem, int device, void* stream);
+
+/* The fusion step of the hybrid retriever in one launch.  Lists are read in place as
+ * ids[p * path_stride + q * query_stride + r] (p < n_paths, r < depth; -1 = padding), device memory:
+ *   path `title_path` (or -1): ids are rows of the title corpus, replaced by title_to_chunk[id] (device int64 [n_titles]);
+ *        several titles may stand for one chunk — the first occurrence counts and the ranks behind it close up
+ *        (the id-level form of src/utils/ensembleRetriever.py:143-150);
+ *   path `sparse_path` (or -1): entries with score <= 0 are dropped (bm25s pads a query that matched fewer than `depth`
+ *        docs with zero-score docs; they must not earn 1/(k_rrf + rank));
+ *   then fused(d) = sum over paths in path order of 1/(k_rrf + rank_p(d)), top k by (fused desc, id asc).
+ * n_paths <= 8, n_paths * depth <= 4096. */
+int vfi_fuse_hybrid(const int64_t* ids, const float* scores, int64_t nq, int n_paths, int depth, int64_t path_stride,
+                    int64_t query_stride, const int64_t* title_to_chunk, int64_t n_titles, int title_path,
+                    int sparse_path, float k_rrf, int k, float* out_scores, int64_t* out_ids, int device, void* stream);
 
 /* ---- query/document text (host only; usable without a CUDA device) --------------------------- */
 /* Snowball "english" (Porter2) stemmer, UTF-8.  words: the concatenated bytes of n_words words, word i =

@@ -69,3 +69,19 @@ def union_python(ids: np.ndarray, scores: np.ndarray):
                 row.append((d, float(scores[b, p, r]), p))
         out.append(row)
     return out
+
+
+def hybrid(ids: np.ndarray, scores: np.ndarray, title_to_chunk, title_path: int, sparse_path: int, k_rrf: float, k: int):
+    """The hybrid fusion step, stage by stage (ids/scores [B,P,L]): title ids -> chunk ids with the first occurrence kept
+    and the ranks closed up (union over that one path), BM25 entries with score <= 0 dropped (bm25s' zero-score filler),
+    then RRF.  Restates what vfi_fuse_hybrid does in one launch."""
+    ids = np.array(ids, dtype=np.int64, copy=True)
+    scores = np.ascontiguousarray(scores, dtype=np.float32)
+    if title_path >= 0:
+        t = ids[:, title_path, :]
+        mapped = np.where(t >= 0, np.asarray(title_to_chunk, dtype=np.int64)[np.clip(t, 0, None)], -1)
+        mi, _, _, _ = union(mapped[:, None, :], scores[:, title_path, :][:, None, :])
+        ids[:, title_path, :] = mi
+    if sparse_path >= 0:
+        ids[:, sparse_path, :] = np.where(scores[:, sparse_path, :] > 0, ids[:, sparse_path, :], -1)
+    return rrf(ids, k_rrf, k)

@@ -63,10 +63,8 @@ def main():
     for r0 in range(0, rows, 1 << 20):
         idx.add(synth.dense_corpus_torch(min(1 << 20, rows - r0), d, 7 + r0 // (1 << 20), DEV))
     qf = synth.dense_queries_torch(batch, d, 7, DEV)
-    variants = [("k1", {N.OPT_TAU_HINT: 1, N.OPT_CLUSTER: 0})]
-    variants += [(f"k1_cluster{c}", {N.OPT_TAU_HINT: 1, N.OPT_CLUSTER: c}) for c in (2, 4, 8)]
-    if hasattr(N, "OPT_CTA_PAIR"):
-        variants += [(f"k1_pair{v}", {N.OPT_TAU_HINT: 1, N.OPT_CLUSTER: 0, N.OPT_CTA_PAIR: v}) for v in (1, 2)]
+    variants = [("k1", {N.OPT_TAU_HINT: 1})]
+    variants += [(f"k1_pair{v}", {N.OPT_TAU_HINT: 1, N.OPT_CTA_PAIR: v}) for v in (1, 2)]
     only = os.environ.get("VFI_PEAK_ONLY")
     for name, opts in variants:
         if only and name not in only.split(","):

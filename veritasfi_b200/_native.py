@@ -11,8 +11,9 @@ from .build import LIB_PATH
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_INTERNAL = range(7)
 MEM_HOST, MEM_DEVICE = 0, 1
 STORE_BF16, STORE_F32 = 0, 1
-OPT_OVERFETCH, OPT_FORCE_PATH, OPT_PROFILE, OPT_TAU_HINT, OPT_NUM_CTAS, OPT_CLUSTER, OPT_CTA_PAIR, OPT_TAIL = 1, 2, 3, 4, 5, 6, 7, 8
-PATH_AUTO, PATH_EXHAUSTIVE, PATH_FUSED, PATH_GEMV = 0, 1, 2, 3
+OPT_OVERFETCH, OPT_FORCE_PATH, OPT_PROFILE, OPT_TAU_HINT, OPT_NUM_CTAS, OPT_CTA_PAIR = 1, 2, 3, 4, 5, 7
+PATH_AUTO, PATH_EXACT, PATH_FUSED, PATH_GEMV = 0, 1, 2, 3
+PATH_EXHAUSTIVE = PATH_EXACT   # the old name: every row scored canonically
 MAX_K = 2048
 IPC_HANDLE_BYTES = 64
 
@@ -85,6 +86,12 @@ _SIGNATURES = {
     "vfi_stem_english": (C.c_int, [C.c_char_p, _P, C.c_int64, _P, C.c_int64, _P]),
     "vfi_tokenize_ascii": (C.c_int, [C.c_char_p, C.c_int64, _P, _P, C.c_int64, _P]),
     "vfi_fuse_union": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "vfi_fuse_hybrid": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int, C.c_int,
+                                  C.c_float, C.c_int, _P, _P, C.c_int, _P]),
+    "vfi_index_ticket_flag": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    "vfi_exchange_merge_flagged": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "vfi_bm25_create_from": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vfi_bm25_rank_range": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -165,17 +165,22 @@ class GpuPostings:
                                              N.MEM_HOST, None))
         return ids, scores
 
-    def search_csr_device(self, toks: np.ndarray, qptr: np.ndarray, k: int, device=None):
+    def search_csr_device(self, toks: np.ndarray, qptr: np.ndarray, k: int, device=None, out=None):
         """Same search with the results left on the GPU: (ids int64 [B,k], scores float32 [B,k]) torch CUDA tensors
-        (the hybrid path hands them straight to the fusion kernel)."""
+        (the hybrid path hands them straight to the fusion kernel).  out: optional contiguous (ids, scores) to write into."""
         import torch
 
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         B = len(qptr) - 1
         toks = np.ascontiguousarray(toks, dtype=np.int32)
         qptr = np.ascontiguousarray(qptr, dtype=np.int64)
-        scores = torch.full((B, k), -float(np.finfo(np.float32).max), dtype=torch.float32, device=dev)
-        ids = torch.full((B, k), -1, dtype=torch.int64, device=dev)
+        if out is None:
+            scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+            ids = torch.empty((B, k), dtype=torch.int64, device=dev)
+        else:
+            ids, scores = out
+            if not (ids.is_contiguous() and scores.is_contiguous() and ids.shape == (B, k) and scores.shape == (B, k)):
+                raise ValueError("search_csr_device: out must be contiguous (int64 [B,k], float32 [B,k])")
         if B:
             N.check(N.load().vfi_bm25_search(self._h, toks.ctypes.data_as(C.c_void_p), qptr.ctypes.data_as(C.c_void_p),
                                              B, int(k), C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()),
@@ -205,6 +210,32 @@ class GpuPostings:
                                            scores.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p), None))
         return ids, scores
 
+    def rank_range(self, tokens: Sequence[int], first: int, count: int):
+        """Ranks [first, first+count) of the full (score desc, id asc) order of one query: the tail behind an eager top-k."""
+        toks = np.ascontiguousarray(tokens, dtype=np.int32)
+        scores = np.zeros(count, dtype=np.float32)
+        ids = np.zeros(count, dtype=np.int64)
+        if count:
+            N.check(N.load().vfi_bm25_rank_range(self._h, toks.ctypes.data_as(C.c_void_p), len(toks), int(first), int(count),
+                                                 scores.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p), None))
+        return ids, scores
+
+    @classmethod
+    def from_device(cls, indptr, indices, data, n_docs: int, id_offset: int = 0) -> "GpuPostings":
+        """Adopt posting arrays that already live on the GPU (torch CUDA tensors: int64 [V+1], int32 [nnz], float32 [nnz]);
+        they are copied device-to-device and validated on the device (vfi_bm25_create_from)."""
+        self = cls.__new__(cls)
+        self.indptr = self.indices = self.data = None
+        self.n_vocab = int(indptr.numel()) - 1
+        self.n_docs = int(n_docs)
+        self.id_offset = int(id_offset)
+        self._h = C.c_void_p()
+        indptr, indices, data = indptr.contiguous(), indices.contiguous(), data.contiguous()
+        N.check(N.load().vfi_bm25_create_from(C.c_void_p(indptr.data_ptr()), C.c_void_p(indices.data_ptr()),
+                                              C.c_void_p(data.data_ptr()), self.n_vocab, self.n_docs, self.id_offset,
+                                              N.MEM_DEVICE, indptr.device.index or 0, C.byref(self._h)))
+        return self
+
     def set_profile(self, on: bool) -> None:
         N.check(N.load().vfi_bm25_set_profile(self._h, int(on)))
 
@@ -223,6 +254,93 @@ class GpuPostings:
             self.close()
         except Exception:
             pass
+
+
+class _Ranking:
+    """The ranking of one query: an eager head (the exact top-h from vfi_bm25_search) and the tail [h, k) produced by
+    vfi_bm25_rank_range the first time somebody reads past the head.  The reference asks for k = N and reads
+    [:bm25_k] (/root/reference/src/utils/ensembleRetriever.py:189-190)."""
+
+    def __init__(self, gp: "GpuPostings", toks, k: int, head_ids: np.ndarray, head_scores: np.ndarray):
+        self.gp, self.toks, self.k = gp, list(toks), int(k)
+        self.ids, self.scores = head_ids, head_scores
+        self.tail_reads = 0
+
+    def upto(self, n: int):
+        if n > len(self.ids):
+            ti, ts = self.gp.rank_range(self.toks, len(self.ids), self.k - len(self.ids))
+            self.ids = np.concatenate([self.ids, ti])
+            self.scores = np.concatenate([self.scores, ts])
+            self.tail_reads += 1
+        return self.ids, self.scores
+
+
+class LazyRow:
+    """One row of a lazy retrieve(k > 2048) result: behaves like the numpy row bm25s returns (len, indexing, slicing,
+    iteration, np.asarray), reading the tail only when an index past the eager head is touched."""
+
+    def __init__(self, ranking: _Ranking, kind: str, corpus=None):
+        self._r, self._kind, self._corpus = ranking, kind, corpus
+
+    def __len__(self):
+        return self._r.k
+
+    def _map(self, ids, scores):
+        if self._kind == "scores":
+            return scores
+        if self._kind == "ids" or self._corpus is None:
+            return ids
+        out = np.empty(len(ids), dtype=object)
+        for j, i in enumerate(ids):
+            out[j] = self._corpus[int(i)]
+        return out
+
+    def __getitem__(self, key):
+        k = self._r.k
+        if isinstance(key, slice):
+            start, stop, step = key.indices(k)
+            hi = max(start, stop) if step > 0 else start + 1
+            ids, scores = self._r.upto(min(k, max(hi, 0)))
+            return self._map(ids[:k][key], scores[:k][key])
+        i = int(key)
+        if i < 0:
+            i += k
+        if not 0 <= i < k:
+            raise IndexError("rank out of range")
+        ids, scores = self._r.upto(i + 1)
+        return self._map(ids[i:i + 1], scores[i:i + 1])[0]
+
+    def __iter__(self):
+        h = min(len(self._r.ids), self._r.k)
+        yield from self._map(self._r.ids[:h], self._r.scores[:h])
+        if h < self._r.k:
+            ids, scores = self._r.upto(self._r.k)
+            yield from self._map(ids[h:self._r.k], scores[h:self._r.k])
+
+    def __array__(self, dtype=None, copy=None):
+        a = self[:]
+        return a if dtype is None else a.astype(dtype)
+
+
+class LazyResult:
+    """[nq, k] view over per-query rankings: result[i] is a LazyRow."""
+
+    def __init__(self, rankings, kind: str, corpus=None):
+        self._rows = [LazyRow(r, kind, corpus) for r in rankings]
+        self.shape = (len(rankings), rankings[0].k if rankings else 0)
+
+    def __len__(self):
+        return len(self._rows)
+
+    def __getitem__(self, i):
+        return self._rows[i]
+
+    def __iter__(self):
+        return iter(self._rows)
+
+    def __array__(self, dtype=None, copy=None):
+        a = np.stack([np.asarray(r) for r in self._rows]) if self._rows else np.empty(self.shape)
+        return a if dtype is None else a.astype(dtype)
 
 
 class BM25:
@@ -360,15 +478,21 @@ class BM25:
                              "(corpus size should be larger than top-k). Please set with a smaller k or increase the size of corpus.")
         lists = self._query_id_lists(query_tokens)
         nq = len(lists)
-        if k <= N.MAX_K // 2:
-            ids, scores = gp.search(lists, k)
-        else:  # k up to N: rank every doc (ensembleRetriever.py:189 asks for k = num_chunk)
-            ids = np.empty((nq, k), dtype=np.int64)
-            scores = np.empty((nq, k), dtype=np.float32)
-            for i, toks in enumerate(lists):
-                ri, rs = gp.rank_all(toks)
-                ids[i], scores[i] = ri[:k], rs[:k]
         corpus = corpus if corpus is not None else self.corpus
+        if k > N.MAX_K:
+            # k up to N (ensembleRetriever.py:189 asks for k = num_chunk and reads [:bm25_k]): the exact top-2048 eagerly
+            # through the top-k kernel, the ranks behind it on demand (vfi_bm25_rank_range)
+            hi, hs = gp.search(lists, N.MAX_K)
+            rankings = [_Ranking(gp, toks, k, hi[i], hs[i]) for i, toks in enumerate(lists)]
+            self.last_rankings = rankings
+            docs = LazyResult(rankings, "docs", corpus)
+            scores = LazyResult(rankings, "scores")
+            if return_as == "tuple":
+                return Results(documents=docs, scores=scores)
+            if return_as == "documents":
+                return docs
+            raise ValueError("return_as must be 'tuple' or 'documents'")
+        ids, scores = gp.search(lists, k)
         if corpus is not None:
             docs = np.empty((nq, k), dtype=object)
             for i in range(nq):

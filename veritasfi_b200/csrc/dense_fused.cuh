@@ -56,7 +56,6 @@ struct DenseParams {
   const float* tau_init;  // [nq] admission hints (rows with score <= hint are ignored) or nullptr
   float* scores_out;      // MODE_STORE: [nq_pad][ld_scores] scores; MODE_CHUNKMAX: [nq_pad][ld_scores] chunk maxima (ld = 8 per tile)
   int64_t ld_scores;
-  int cluster;            // CTAs per cluster (1, 2, 4 or 8; divides n_mtiles): they share each corpus tile by TMA multicast
 };
 
 // One 32-column chunk of one query's scores against its admission threshold: admitted (score, id) keys are
@@ -213,7 +212,7 @@ dense_fused_kernel(const __grid_constant__ CUtensorMap tmap_q,
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], p.cluster);   // every CTA of the cluster must have consumed the stage
+      ptx::mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
@@ -227,11 +226,8 @@ dense_fused_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (p.cluster > 1) ptx::cluster_sync_all();     // barriers of every peer are initialised before any multicast
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t crank = (p.cluster > 1) ? ptx::cluster_ctarank() : 0u;
-  const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1u);
 
   const int m_tile = static_cast<int>(blockIdx.x) % p.n_mtiles;
   const int group = static_cast<int>(blockIdx.x) / p.n_mtiles;
@@ -241,21 +237,14 @@ dense_fused_kernel(const __grid_constant__ CUtensorMap tmap_q,
   if (active && warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     uint32_t stage = 0, phase = 0;
-    const uint64_t d_hint = (p.n_mtiles > p.cluster) ? ptx::kEvictNormal : ptx::kEvictFirst;
+    const uint64_t d_hint = (p.n_mtiles > 1) ? ptx::kEvictNormal : ptx::kEvictFirst;
     for (int t = group; t < p.n_tiles; t += p.n_groups) {
       for (int kb = 0; kb < nkb; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         ptx::mbar_expect_tx(&full_bar[stage], kABytes + kBBytes);
         ptx::tma_load_2d(sA + stage * kABytes, &tmap_q, &full_bar[stage], kb * kBK,
                          m_tile * kBM, ptx::kEvictLast);
-        if (p.cluster == 1) {
-          ptx::tma_load_2d(sB + stage * kBBytes, &tmap_d, &full_bar[stage], kb * kBK, t * kBN, d_hint);
-        } else {
-          // this CTA fetches rows [rank*256/C, (rank+1)*256/C) of the corpus tile for the whole cluster
-          const int rows = kBN / p.cluster;
-          ptx::tma_load_2d_mcast(sB + stage * kBBytes + crank * rows * 128, &tmap_d, &full_bar[stage], kb * kBK,
-                                 t * kBN + static_cast<int>(crank) * rows, cmask, d_hint);
-        }
+        ptx::tma_load_2d(sB + stage * kBBytes, &tmap_d, &full_bar[stage], kb * kBK, t * kBN, d_hint);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -278,8 +267,7 @@ dense_fused_kernel(const __grid_constant__ CUtensorMap tmap_q,
                             ptx::umma_desc_k128(b_addr + k * 32), idesc,
                             (kb | k) != 0 ? 1u : 0u);
         }
-        if (p.cluster == 1) ptx::tc_commit(&empty_bar[stage]);   // frees the smem stage when MMAs retire
-        else ptx::tc_commit_mcast(&empty_bar[stage], cmask);      // ... in every CTA that multicasts into it
+        ptx::tc_commit(&empty_bar[stage]);   // frees the smem stage when MMAs retire
         if (kb == nkb - 1) ptx::tc_commit(&tfull_bar[acc]);  // accumulator complete
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -291,10 +279,9 @@ dense_fused_kernel(const __grid_constant__ CUtensorMap tmap_q,
                          [&](uint32_t a) { ptx::mbar_arrive(&tempty_bar[a]); });
   }
 
-  // teardown (no CTA may leave while a peer can still multicast into it or signal its barriers)
+  // teardown
   ptx::tc_fence_before();
   __syncthreads();
-  if (p.cluster > 1) ptx::cluster_sync_all();
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);

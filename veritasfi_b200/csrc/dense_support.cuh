@@ -12,6 +12,7 @@
 #include <cuda_bf16.h>
 
 #include "ptx.cuh"
+#include "reduce.cuh"
 #include "select.cuh"
 #include "topk_common.cuh"
 
@@ -134,88 +135,6 @@ __global__ void normalize_l2_kernel(float* __restrict__ x, int64_t n, int d) {
   if (nrm2 > 0.f) {
     const float inv = 1.0f / sqrtf(nrm2);
     for (int j = lane; j < d; j += 32) xr[j] = xr[j] * inv;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// K1c: union of the per-group candidate buffers of one query -> the k' best keys, sorted.
-// bound[q] = an upper bound on the tensor-core score of every row that is NOT in the output:
-//   the k'-th key's score when at least k' rows were admitted, else the admission hint (rows at
-//   or below the hint were never admitted), else -inf (every row of the shard is a candidate).
-// ------------------------------------------------------------------------------------------
-struct GroupBufSrc {
-  const uint64_t* cand;
-  const uint32_t* pref;   // shared memory: exclusive prefix of the per-group counts, [n_groups + 1]
-  int n_groups, nq_pad, cap, q;
-  template <class F>
-  __device__ void for_each(F f) const {
-    // flat index -> (group, offset) by binary search in the prefix array; four independent loads in flight per thread
-    const uint32_t total = pref[n_groups];
-    auto locate = [&](uint32_t i) -> const uint64_t* {
-      int lo = 0, hi = n_groups;
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (pref[mid] <= i) lo = mid; else hi = mid;
-      }
-      return cand + (static_cast<size_t>(lo) * nq_pad + q) * cap + (i - pref[lo]);
-    };
-    uint32_t i = threadIdx.x;
-    const uint32_t stride = blockDim.x;
-    for (; i + 3 * stride < total; i += 4 * stride) {
-      uint64_t v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = *locate(i + j * stride);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) f(v[j]);
-    }
-    for (; i < total; i += stride) f(*locate(i));
-  }
-};
-
-using CandSmem = SelectSmemT<1024>;   // 8 KB of keys: seven CTAs per SM, so 1024 queries are one wave (k' <= 256 only)
-template <class SM>
-__global__ void __launch_bounds__(256, (sizeof(SM) <= 16384 ? 7 : 4)) cand_reduce_kernel(const uint64_t* __restrict__ cand,
-                                                          const uint32_t* __restrict__ cnt,
-                                                          int n_groups, int nq_pad, int cap,
-                                                          int keep, const float* __restrict__ tau_init,
-                                                          uint64_t* __restrict__ out_keys,
-                                                          uint32_t* __restrict__ out_n,
-                                                          float* __restrict__ bound) {
-  extern __shared__ uint8_t smem_raw[];
-  SM* sm = reinterpret_cast<SM*>(smem_raw);
-  const int q = blockIdx.x;
-  __shared__ uint32_t s_pref[1025];
-  // counts of all group buffers in one coalesced sweep, then an exclusive scan (n_groups <= 1024)
-  for (int g = threadIdx.x; g < n_groups; g += blockDim.x)
-    s_pref[g + 1] = min(cnt[static_cast<size_t>(g) * nq_pad + q], static_cast<uint32_t>(cap));
-  if (threadIdx.x == 0) s_pref[0] = 0;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    uint32_t carry = 0;
-    for (int base = 0; base < n_groups; base += 32) {
-      const int g = base + threadIdx.x;
-      uint32_t v = (g < n_groups) ? s_pref[g + 1] : 0u;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
-        if (static_cast<int>(threadIdx.x) >= o) v += t;
-      }
-      if (g < n_groups) s_pref[g + 1] = v + carry;
-      carry += __shfl_sync(0xFFFFFFFFu, v, 31);
-    }
-  }
-  __syncthreads();
-  const uint32_t total = s_pref[n_groups];
-  GroupBufSrc src{cand, s_pref, n_groups, nq_pad, cap, q};
-  const uint32_t n = block_topk(src, total, static_cast<uint32_t>(keep), sm);
-  for (uint32_t i = threadIdx.x; i < static_cast<uint32_t>(keep); i += blockDim.x)
-    out_keys[static_cast<size_t>(q) * keep + i] = (i < n) ? sm->keys[i] : kKeyNone;
-  if (threadIdx.x == 0) {
-    out_n[q] = n;
-    float b;
-    if (total >= static_cast<uint32_t>(keep)) b = key_score(sm->keys[keep - 1]);
-    else b = (tau_init != nullptr) ? tau_init[q] : -INFINITY;
-    bound[q] = b;
   }
 }
 
@@ -383,57 +302,6 @@ __global__ void __launch_bounds__(128) canon_score_kernel(
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// K2b: final order + certificate.  One CTA per selected query.
-// The result is provably the exact top-k iff every excluded row r satisfies
-//   exact(r) <= tc(r) + eps <= bound + eps < exact k-th of the candidates.
-// Queries failing the test are appended to `flagged` for the exhaustive pass.
-// ------------------------------------------------------------------------------------------
-struct KeyArraySrc {
-  const uint64_t* keys;
-  int64_t n;
-  template <class F>
-  __device__ void for_each(F f) const {
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint64_t k = keys[i];
-      if (k != kKeyNone) f(k);
-    }
-  }
-};
-
-__global__ void __launch_bounds__(256) finalize_kernel(
-    const uint64_t* __restrict__ keys2, int64_t keys2_pitch, int64_t n_slots,
-    const int* __restrict__ qsel, const uint32_t* __restrict__ n_cand, int k, int64_t id_offset,
-    const float* __restrict__ bound, const float* __restrict__ eps, int check,
-    float* __restrict__ out_scores, int64_t* __restrict__ out_ids, int* __restrict__ flagged,
-    int* __restrict__ n_flagged) {
-  extern __shared__ uint8_t smem_raw[];
-  SelectSmem* sm = reinterpret_cast<SelectSmem*>(smem_raw);
-  const int qslot = blockIdx.x;
-  const int q = (qsel != nullptr) ? qsel[qslot] : qslot;
-  const uint32_t total = (n_cand != nullptr) ? n_cand[q] : static_cast<uint32_t>(n_slots);
-  KeyArraySrc src{keys2 + static_cast<int64_t>(qslot) * keys2_pitch, n_slots};
-  const uint32_t n = block_topk(src, total, static_cast<uint32_t>(k), sm);
-  bool ok = true;
-  if (check) {
-    const float b = bound[q];
-    if (b != -INFINITY) {
-      if (n < static_cast<uint32_t>(k)) ok = false;
-      else ok = key_score(sm->keys[k - 1]) > b + eps[q];
-    }
-  }
-  if (ok) {
-    for (int i = threadIdx.x; i < k; i += blockDim.x) {
-      const bool has = static_cast<uint32_t>(i) < n;
-      const uint64_t key = has ? sm->keys[i] : 0ull;
-      out_scores[static_cast<int64_t>(q) * k + i] = has ? key_score(key) : -3.402823466e+38f;
-      out_ids[static_cast<int64_t>(q) * k + i] = has ? static_cast<int64_t>(key_id(key)) + id_offset : -1;
-    }
-  } else if (threadIdx.x == 0) {
-    flagged[atomicAdd(n_flagged, 1)] = q;
-  }
-}
-
 // stored rows -> fp32 (bulk reconstruct) ; one thread per element
 template <typename RowT>
 __global__ void rows_to_f32_kernel(const RowT* __restrict__ rows, int64_t pitch, int64_t first, int64_t n, int d,
@@ -461,94 +329,6 @@ __global__ void gather_rows_kernel(const RowT* __restrict__ rows, int64_t pitch,
 __global__ void keys_to_scores_kernel(const uint64_t* __restrict__ keys, int64_t n, float* __restrict__ out) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = key_score(keys[i]);
-}
-
-// ------------------------------------------------------------------------------------------
-// K1c+K2 fused (k' <= 256): one CTA per query does the whole tail of a search — union of the group
-// buffers, k' best by tensor-core score, canonical rescoring (warps 0-3, 32 candidates each per round),
-// final order, certificate, output.  Saves two launches and the round trips through global memory.
-// ------------------------------------------------------------------------------------------
-struct TailSmem {
-  SelectSmem sel;
-  uint32_t pref[1025];
-  uint32_t tile[4][32 * kCanonPitch];
-  double qs[4][128];
-};
-
-template <typename RowT>
-__global__ void __launch_bounds__(256, 3) select_rescore_kernel(
-    const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, int n_groups, int nq_pad, int cap, int keep,
-    const float* __restrict__ tau_init, const RowT* __restrict__ rows, int64_t row_pitch, int dp,
-    const float* __restrict__ qcanon, int k, int64_t id_offset, const float* __restrict__ eps,
-    float* __restrict__ out_scores, int64_t* __restrict__ out_ids, int* __restrict__ flagged, int* __restrict__ n_flagged,
-    uint32_t* __restrict__ max_err_bits) {
-  extern __shared__ uint8_t smem_raw[];
-  TailSmem* ts = reinterpret_cast<TailSmem*>(smem_raw);
-  SelectSmem* sm = &ts->sel;
-  const int q = blockIdx.x;
-  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int g = tid; g < n_groups; g += blockDim.x)
-    ts->pref[g + 1] = min(cnt[static_cast<size_t>(g) * nq_pad + q], static_cast<uint32_t>(cap));
-  if (tid == 0) ts->pref[0] = 0;
-  __syncthreads();
-  if (tid < 32) {
-    uint32_t carry = 0;
-    for (int base = 0; base < n_groups; base += 32) {
-      const int g = base + tid;
-      uint32_t v = (g < n_groups) ? ts->pref[g + 1] : 0u;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
-        if (static_cast<int>(tid) >= o) v += t;
-      }
-      if (g < n_groups) ts->pref[g + 1] = v + carry;
-      carry += __shfl_sync(0xFFFFFFFFu, v, 31);
-    }
-  }
-  __syncthreads();
-  const uint32_t total = ts->pref[n_groups];
-  GroupBufSrc src{cand, ts->pref, n_groups, nq_pad, cap, q};
-  const uint32_t n = block_topk(src, total, static_cast<uint32_t>(keep), sm);   // sm->keys[0..n) sorted by tensor-core score
-  float bound;
-  if (total >= static_cast<uint32_t>(keep)) bound = key_score(sm->keys[keep - 1]);
-  else bound = (tau_init != nullptr) ? tau_init[q] : -INFINITY;
-  __syncthreads();
-  // canonical rescoring into the upper half of the key array (n <= keep <= 256)
-  uint64_t* keys2 = sm->keys + 2048;
-  if (warp < 4) {
-    for (uint32_t first = warp * 32; first < n; first += 128) {
-      const uint32_t slot = first + lane;
-      const bool valid = slot < n;
-      uint32_t id = 0;
-      float tc = 0.f;
-      if (valid) { id = key_id(sm->keys[slot]); tc = key_score(sm->keys[slot]); }
-      const float s = canon_dot_warp<RowT>(rows, row_pitch, dp, qcanon + static_cast<int64_t>(q) * dp, id, valid,
-                                                 ts->tile[warp], ts->qs[warp], lane);
-      if (valid) {
-        keys2[slot] = make_key(s, id);
-        if (max_err_bits != nullptr) atomicMax(max_err_bits, __float_as_uint(fabsf(s - tc)));
-      }
-    }
-  }
-  __syncthreads();
-  const uint32_t np = max(next_pow2(n), 2u);
-  for (uint32_t i = tid; i < np; i += blockDim.x) sm->keys[i] = (i < n) ? keys2[i] : 0ull;
-  block_bitonic_desc(sm->keys, np);
-  bool ok = true;
-  if (bound != -INFINITY) {
-    if (n < static_cast<uint32_t>(k)) ok = false;
-    else ok = key_score(sm->keys[k - 1]) > bound + eps[q];
-  }
-  if (ok) {
-    for (int i = tid; i < k; i += blockDim.x) {
-      const bool has = static_cast<uint32_t>(i) < n;
-      const uint64_t key = has ? sm->keys[i] : 0ull;
-      out_scores[static_cast<int64_t>(q) * k + i] = has ? key_score(key) : -3.402823466e+38f;
-      out_ids[static_cast<int64_t>(q) * k + i] = has ? static_cast<int64_t>(key_id(key)) + id_offset : -1;
-    }
-  } else if (tid == 0) {
-    flagged[atomicAdd(n_flagged, 1)] = q;
-  }
 }
 
 // ------------------------------------------------------------------------------------------

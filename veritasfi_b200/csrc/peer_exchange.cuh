@@ -6,10 +6,13 @@
 // single launch per rank does:
 //   push   — the CTA that owns query q packs its k results into 64-bit keys and stores them straight into
 //            slot [parity][my rank][q] of EVERY rank's window (remote stores over NVLink, 2 KB coalesced
-//            bursts), then publishes them with a system-scope release store of the epoch number into
-//            flag [parity][my rank][q] of that rank;
+//            bursts), then publishes them with a system-scope release store of (epoch << 1 | fail) into
+//            flag [parity][my rank][q] of that rank — `fail` says that this rank's exactness certificate
+//            flagged some query of the batch, i.e. the rows it is pushing may still be repaired;
 //   wait   — the same CTA acquires flag [parity][r][q] of its own window for every rank r;
-//   merge  — and selects the k_out best of the world*k keys now sitting in local HBM/L2.
+//   merge  — and selects the k_out best of the world*k keys now sitting in local HBM/L2; the OR of the fail
+//            bits of all ranks goes to *any_fail, the same value on every rank, so the ranks agree on whether
+//            the batch has to be exchanged again after the repair (pipelined sharded search, sharded.py).
 // No CTA ever waits on another CTA of its own grid, and the grid is sized to be fully resident, so the
 // only dependency is "the peer has reached the same exchange", exactly the dependency of a collective.
 // Windows are double-buffered by epoch parity: a rank can only start epoch e+2 after its own epoch e+1
@@ -36,6 +39,9 @@ struct ExchangeParams {
   const int64_t* ids;           // global ids, -1 = padding
   float* out_scores;            // [nq][k_out]
   int64_t* out_ids;
+  const int* fail_a;            // device: > 0 when this rank's local results are not final yet (may be null)
+  const int* fail_b;
+  int* any_fail;                // device: set to 1 when any rank reported fail (may be null)
   unsigned long long timeout_ns;
 };
 
@@ -78,6 +84,10 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const ExchangeParam
   const int64_t par_keys = static_cast<int64_t>(p.world) * slot_keys;
   const int64_t par_flags = static_cast<int64_t>(p.world) * p.max_nq;
 
+  const uint32_t my_fail = ((p.fail_a != nullptr && *p.fail_a > 0) || (p.fail_b != nullptr && *p.fail_b > 0)) ? 1u : 0u;
+  const uint32_t stamp = (p.epoch << 1) | my_fail;
+  __shared__ uint32_t s_fail;
+  if (threadIdx.x == 0) s_fail = 0;
   // ---- push: all queries of this CTA first, so the stores of every query are in flight together
   for (int q = blockIdx.x; q < p.nq; q += gridDim.x) {
     for (int j = threadIdx.x; j < p.k; j += blockDim.x) {
@@ -92,7 +102,7 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const ExchangeParam
     __syncthreads();
     if (threadIdx.x < static_cast<uint32_t>(p.world)) {
       const int r = (p.rank + threadIdx.x) % p.world;
-      st_release_sys_u32(p.flags[r] + parity * par_flags + static_cast<int64_t>(p.rank) * p.max_nq + q, p.epoch);
+      st_release_sys_u32(p.flags[r] + parity * par_flags + static_cast<int64_t>(p.rank) * p.max_nq + q, stamp);
     }
   }
   // ---- wait + merge
@@ -102,11 +112,12 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const ExchangeParam
     if (threadIdx.x < static_cast<uint32_t>(p.world)) {
       const uint32_t* f = my_flags + static_cast<int64_t>(threadIdx.x) * p.max_nq + q;
       const unsigned long long t0 = global_timer_ns();
-      uint32_t spins = 0;
-      while (ld_acquire_sys_u32(f) != p.epoch) {
+      uint32_t spins = 0, v;
+      while (((v = ld_acquire_sys_u32(f)) >> 1) != p.epoch) {
         // a peer that never arrives (crashed rank, mismatched call sequence) must not hang the GPU
         if ((++spins & 0x3FFu) == 0u && global_timer_ns() - t0 > p.timeout_ns) __trap();
       }
+      if (v & 1u) s_fail = 1;
     }
     __syncthreads();
     WindowSrc src{my_win, p.world, p.k, q, p.max_nq, p.max_k};
@@ -119,6 +130,7 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const ExchangeParam
     }
     __syncthreads();   // sm is reused by the next query
   }
+  if (threadIdx.x == 0 && s_fail != 0 && p.any_fail != nullptr) *p.any_fail = 1;
 }
 
 }  // namespace vfi

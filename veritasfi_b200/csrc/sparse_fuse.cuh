@@ -26,7 +26,7 @@ namespace vfi {
 // no speculation and no per-tile bookkeeping.
 constexpr int kBmRange = 8192;    // docs per range (32 KB accumulator)
 constexpr int kBmThreads = 256;
-constexpr int kBmMaxTok = 64;     // tokens per query handled by the kernel
+constexpr int kBmMaxTok = 64;     // tokens applied per chunk (longer queries take several chunks per range)
 constexpr int kBmMaxRanges = 8;   // ranges per segment
 constexpr int kBmScan = 1024;     // docs scanned between buffer-compaction checks
 constexpr int kBmUnroll = 8;      // postings per thread in flight while a heavy token streams
@@ -95,13 +95,19 @@ __global__ void __launch_bounds__(kBmThreads, 4) bm25_kernel(const Bm25Params p)
     const int64_t d1 = min(d0 + p.seg_docs, p.n_docs);
     const int R = static_cast<int>((d1 - d0 + kBmRange - 1) / kBmRange);
     const int64_t tq0 = p.q_indptr[q];
-    const int T = static_cast<int>(p.q_indptr[q + 1] - tq0);
-    // every (token, range boundary) offset by an independent binary search
-    for (int i = tid; i < T * (R + 1); i += kBmThreads) {
-      const int t = i / (R + 1), r = i % (R + 1);
-      const int32_t tok = p.q_tokens[tq0 + t];
-      const int64_t bound = min(d0 + static_cast<int64_t>(r) * kBmRange, d1);
-      sm->offs[t][r] = lower_bound_i32(p.indices, p.indptr[tok], p.indptr[tok + 1], bound);
+    const int T_all = static_cast<int>(p.q_indptr[q + 1] - tq0);
+    // Queries of more than kBmMaxTok tokens are applied in chunks of kBmMaxTok tokens, chunk after chunk inside every
+    // range (the per-doc add order stays query-token order); their posting offsets are searched per (range, chunk)
+    // instead of once per work item.  bm25s has no token limit (the reference sends paragraph-length rewritten queries).
+    const int n_chunks = max(1, (T_all + kBmMaxTok - 1) / kBmMaxTok);
+    if (n_chunks == 1) {
+      // every (token, range boundary) offset by an independent binary search
+      for (int i = tid; i < T_all * (R + 1); i += kBmThreads) {
+        const int t = i / (R + 1), r = i % (R + 1);
+        const int32_t tok = p.q_tokens[tq0 + t];
+        const int64_t bound = min(d0 + static_cast<int64_t>(r) * kBmRange, d1);
+        sm->offs[t][r] = lower_bound_i32(p.indices, p.indptr[tok], p.indptr[tok + 1], bound);
+      }
     }
     if (tid == 0) { sm->count = 0; sm->tau = (p.qtau != nullptr) ? p.qtau[q] : kKeyNone; }
     for (int i = tid; i < kBmRange; i += kBmThreads) sm->acc[i] = 0.f;
@@ -111,111 +117,126 @@ __global__ void __launch_bounds__(kBmThreads, 4) bm25_kernel(const Bm25Params p)
       const int64_t rs = d0 + static_cast<int64_t>(r) * kBmRange;
       const int64_t re = min(rs + kBmRange, d1);
       const int range_docs = static_cast<int>(re - rs);
-      // Per-range bookkeeping by warp 0 (T <= 64: two tokens per lane): posting counts, light/streamed classification
-      // by ballot, the first kBmLight light tokens in token order.  A light token has at most kBmThreads postings in the
-      // range: thread i prefetches its i-th posting, all light tokens at once, so their latencies overlap; heavier
-      // tokens (and light ones beyond kBmLight) are streamed when their turn comes.
-      if (tid < 32) {
-        uint32_t sum = 0;
-        uint32_t light_before = 0;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int t = half * 32 + static_cast<int>(tid);
-          const uint32_t c = (t < T) ? static_cast<uint32_t>(sm->offs[t][r + 1] - sm->offs[t][r]) : 0u;
-          const bool light = c > 0 && c <= static_cast<uint32_t>(kBmThreads);
-          const uint32_t lmask = __ballot_sync(0xFFFFFFFFu, light);
-          const uint32_t ord = light_before + __popc(lmask & ((1u << tid) - 1u));
-          if (t < T) {
-            sm->cnt[t] = c;
-            sm->kind[t] = (c == 0) ? 0 : ((light && ord < static_cast<uint32_t>(kBmLight)) ? 1 : 2);
-            if (light && ord < static_cast<uint32_t>(kBmLight)) sm->ltok[ord] = static_cast<uint8_t>(t);
-          }
-          light_before += __popc(lmask);
-          sum += c;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-        if (tid == 0) {
-          sm->total = sum;
-          sm->n_light = static_cast<int>(min(light_before, static_cast<uint32_t>(kBmLight)));
-          sm->overflow = 0;
-          if (p.qtau != nullptr) {     // adopt a better threshold published by another segment of this query
-            const uint64_t g = *reinterpret_cast<volatile unsigned long long*>(p.qtau + q);
-            if (g > sm->tau) sm->tau = g;
-          }
-        }
-      }
-      __syncthreads();
-      if (sm->total == 0 && p.all_positive && p.dump == nullptr) {   // no token touches this range
-        __syncthreads();                                               // (everyone has read total before it is rewritten)
-        continue;
-      }
-      const int n_light = sm->n_light;
-      int32_t ldoc[kBmLight];
-      float lval[kBmLight];
-#pragma unroll
-      for (int u = 0; u < kBmLight; ++u) {
-        ldoc[u] = -1;
-        lval[u] = 0.f;
-        if (u < n_light) {
-          const int t = sm->ltok[u];
-          if (tid < sm->cnt[t]) {
-            const int64_t o = sm->offs[t][r] + tid;
-            ldoc[u] = __ldg(p.indices + o);
-            lval[u] = __ldg(p.data + o);
-          }
-        }
-      }
       float* acc = sm->acc - rs;                    // acc[doc] for docs of this range
-      // Stream one token: coalesced 4-byte loads, kBmUnroll postings per thread in flight; adjacent lanes hold ADJACENT
-      // postings, i.e. ascending (for heavy tokens consecutive) docs, so the read-modify-write of the accumulator is
-      // free of bank conflicts.  Inside one token every doc occurs once: the adds of different threads never collide.
-      auto stream = [&](int t) {
-        const uint32_t n = sm->cnt[t];
-        const int32_t* ip = p.indices + sm->offs[t][r] + tid;
-        const float* dp = p.data + sm->offs[t][r] + tid;
-        uint32_t i = tid;
-        for (; i + (kBmUnroll - 1) * kBmThreads < n; i += kBmUnroll * kBmThreads) {
-          int32_t dd[kBmUnroll];
-          float vv[kBmUnroll];
-#pragma unroll
-          for (int u = 0; u < kBmUnroll; ++u) { dd[u] = __ldg(ip + u * kBmThreads); vv[u] = __ldg(dp + u * kBmThreads); }
-#pragma unroll
-          for (int u = 0; u < kBmUnroll; ++u) acc[dd[u]] += vv[u];
-          ip += kBmUnroll * kBmThreads;
-          dp += kBmUnroll * kBmThreads;
+      bool touched = false;
+      for (int tc = 0; tc < n_chunks; ++tc) {
+        const int tb = tc * kBmMaxTok;
+        const int T = min(kBmMaxTok, T_all - tb);
+        if (n_chunks > 1) {
+          for (int i = tid; i < T * 2; i += kBmThreads) {
+            const int t = i >> 1, e = i & 1;
+            const int32_t tok = p.q_tokens[tq0 + tb + t];
+            sm->offs[t][r + e] = lower_bound_i32(p.indices, p.indptr[tok], p.indptr[tok + 1], e ? re : rs);
+          }
+          __syncthreads();
         }
-        if (i < n) {
-          int32_t dd[kBmUnroll];
-          float vv[kBmUnroll];
+        // Per-range bookkeeping by warp 0 (T <= 64: two tokens per lane): posting counts, light/streamed classification
+        // by ballot, the first kBmLight light tokens in token order.  A light token has at most kBmThreads postings in the
+        // range: thread i prefetches its i-th posting, all light tokens at once, so their latencies overlap; heavier
+        // tokens (and light ones beyond kBmLight) are streamed when their turn comes.
+        if (tid < 32) {
+          uint32_t sum = 0;
+          uint32_t light_before = 0;
 #pragma unroll
-          for (int u = 0; u < kBmUnroll; ++u) {
-            dd[u] = -1;
-            vv[u] = 0.f;
-            if (i + u * kBmThreads < n) { dd[u] = __ldg(ip + u * kBmThreads); vv[u] = __ldg(dp + u * kBmThreads); }
+          for (int half = 0; half < 2; ++half) {
+            const int t = half * 32 + static_cast<int>(tid);
+            const uint32_t c = (t < T) ? static_cast<uint32_t>(sm->offs[t][r + 1] - sm->offs[t][r]) : 0u;
+            const bool light = c > 0 && c <= static_cast<uint32_t>(kBmThreads);
+            const uint32_t lmask = __ballot_sync(0xFFFFFFFFu, light);
+            const uint32_t ord = light_before + __popc(lmask & ((1u << tid) - 1u));
+            if (t < T) {
+              sm->cnt[t] = c;
+              sm->kind[t] = (c == 0) ? 0 : ((light && ord < static_cast<uint32_t>(kBmLight)) ? 1 : 2);
+              if (light && ord < static_cast<uint32_t>(kBmLight)) sm->ltok[ord] = static_cast<uint8_t>(t);
+            }
+            light_before += __popc(lmask);
+            sum += c;
           }
 #pragma unroll
-          for (int u = 0; u < kBmUnroll; ++u)
-            if (dd[u] >= 0) acc[dd[u]] += vv[u];
-        }
-      };
-      // tokens in query order, a block barrier after each (token t fully applied before token t+1 touches the same
-      // docs): the prefetched light tokens are walked by a compile-time index, streamed tokens in between
-      {
-        int t = 0;
-#pragma unroll
-        for (int u = 0; u <= kBmLight; ++u) {
-          const int tl = (u < n_light) ? static_cast<int>(sm->ltok[u < kBmLight ? u : 0]) : T;
-          for (; t < tl; ++t) {
-            if (sm->kind[t] == 2) { stream(t); __syncthreads(); }
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+          if (tid == 0) {
+            sm->total = sum;
+            sm->n_light = static_cast<int>(min(light_before, static_cast<uint32_t>(kBmLight)));
+            sm->overflow = 0;
+            if (p.qtau != nullptr && tc == 0) {     // adopt a better threshold published by another segment of this query
+              const uint64_t g = *reinterpret_cast<volatile unsigned long long*>(p.qtau + q);
+              if (g > sm->tau) sm->tau = g;
+            }
           }
-          if (u < kBmLight && u < n_light) {
-            if (ldoc[u] >= 0) acc[ldoc[u]] += lval[u];
-            __syncthreads();
-            t = tl + 1;
+        }
+        __syncthreads();
+        if (sm->total == 0) {                          // no token of this chunk touches the range
+          __syncthreads();                             // (everyone has read total before it is rewritten)
+          continue;
+        }
+        touched = true;
+        const int n_light = sm->n_light;
+        int32_t ldoc[kBmLight];
+        float lval[kBmLight];
+#pragma unroll
+        for (int u = 0; u < kBmLight; ++u) {
+          ldoc[u] = -1;
+          lval[u] = 0.f;
+          if (u < n_light) {
+            const int t = sm->ltok[u];
+            if (tid < sm->cnt[t]) {
+              const int64_t o = sm->offs[t][r] + tid;
+              ldoc[u] = __ldg(p.indices + o);
+              lval[u] = __ldg(p.data + o);
+            }
+          }
+        }
+        // Stream one token: coalesced 4-byte loads, kBmUnroll postings per thread in flight; adjacent lanes hold ADJACENT
+        // postings, i.e. ascending (for heavy tokens consecutive) docs, so the read-modify-write of the accumulator is
+        // free of bank conflicts.  Inside one token every doc occurs once: the adds of different threads never collide.
+        auto stream = [&](int t) {
+          const uint32_t n = sm->cnt[t];
+          const int32_t* ip = p.indices + sm->offs[t][r] + tid;
+          const float* dp = p.data + sm->offs[t][r] + tid;
+          uint32_t i = tid;
+          for (; i + (kBmUnroll - 1) * kBmThreads < n; i += kBmUnroll * kBmThreads) {
+            int32_t dd[kBmUnroll];
+            float vv[kBmUnroll];
+#pragma unroll
+            for (int u = 0; u < kBmUnroll; ++u) { dd[u] = __ldg(ip + u * kBmThreads); vv[u] = __ldg(dp + u * kBmThreads); }
+#pragma unroll
+            for (int u = 0; u < kBmUnroll; ++u) acc[dd[u]] += vv[u];
+            ip += kBmUnroll * kBmThreads;
+            dp += kBmUnroll * kBmThreads;
+          }
+          if (i < n) {
+            int32_t dd[kBmUnroll];
+            float vv[kBmUnroll];
+#pragma unroll
+            for (int u = 0; u < kBmUnroll; ++u) {
+              dd[u] = -1;
+              vv[u] = 0.f;
+              if (i + u * kBmThreads < n) { dd[u] = __ldg(ip + u * kBmThreads); vv[u] = __ldg(dp + u * kBmThreads); }
+            }
+#pragma unroll
+            for (int u = 0; u < kBmUnroll; ++u)
+              if (dd[u] >= 0) acc[dd[u]] += vv[u];
+          }
+        };
+        // tokens in query order, a block barrier after each (token t fully applied before token t+1 touches the same
+        // docs): the prefetched light tokens are walked by a compile-time index, streamed tokens in between
+        {
+          int t = 0;
+#pragma unroll
+          for (int u = 0; u <= kBmLight; ++u) {
+            const int tl = (u < n_light) ? static_cast<int>(sm->ltok[u < kBmLight ? u : 0]) : T;
+            for (; t < tl; ++t) {
+              if (sm->kind[t] == 2) { stream(t); __syncthreads(); }
+            }
+            if (u < kBmLight && u < n_light) {
+              if (ldoc[u] >= 0) acc[ldoc[u]] += lval[u];
+              __syncthreads();
+              t = tl + 1;
+            }
           }
         }
       }
+      if (!touched && p.all_positive && p.dump == nullptr) continue;   // all-positive impacts: untouched docs score 0
 
       if (p.dump != nullptr) {
         for (int i = tid; i < kBmRange; i += kBmThreads) {
@@ -270,9 +291,9 @@ __global__ void __launch_bounds__(kBmThreads, 4) bm25_kernel(const Bm25Params p)
           }
           // overflow: some keys of this range were dropped.  Raise the threshold to just below the k'-th
           // stored key, drop the survivors that belong to this range (the rescan re-admits them) and rescan.
-          uint64_t mine[4];                       // kept <= 1024 = 4 per thread
+          uint64_t mine[8];                       // kept <= 2048 = 8 per thread
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 8; ++j) {
             const uint32_t i = tid + j * kBmThreads;
             mine[j] = (i < kept) ? skeys[i] : 0ull;
           }
@@ -286,7 +307,7 @@ __global__ void __launch_bounds__(kBmThreads, 4) bm25_kernel(const Bm25Params p)
           }
           __syncthreads();
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 8; ++j) {
             if (mine[j] != 0ull) {
               const int64_t id = key_id(mine[j]);
               if (id < rs || id >= re) skeys[atomicAdd(&sm->count, 1u)] = mine[j];
@@ -521,6 +542,141 @@ __global__ void __launch_bounds__(256) union_kernel(const int64_t* __restrict__ 
   }
   __syncthreads();
   if (threadIdx.x == 0) out_count[q] = static_cast<int32_t>(sm->ctr);
+}
+
+// ------------------------------------------------------------------------------------------
+// K5c: the fusion step of the hybrid retriever in ONE launch (one CTA per query):
+//   title path   ids are rows of the title-summary corpus: mapped to the chunk each title stands for (the stand-in for
+//                the title -> chunks lookup of /root/reference/src/utils/ensembleRetriever.py:143-145); several titles
+//                can stand for one chunk: the first (best-ranked) occurrence counts and the ranks behind it close up
+//   sparse path  entries with score <= 0 are dropped: with all-positive impacts they are the zero-score filler docs
+//                bm25s' top-k pads with when a query matches fewer than `depth` docs, and must not earn 1/(60+rank)
+//   then RRF     fused(d) = sum over paths (in path order) of 1/(k_rrf + rank_p(d)) in fp32; top k by (fused desc, id asc).
+// Lists are addressed as ids[p * path_stride + q * query_stride + r], so both [B,P,L] and the path-major [P,B,L] layout
+// the sharded exchange produces are read in place.  n_paths * depth <= kSortCap.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hybrid_fuse_kernel(const int64_t* __restrict__ ids, const float* __restrict__ scores,
+                                                          int n_paths, int depth, int64_t path_stride, int64_t query_stride,
+                                                          const int64_t* __restrict__ title_to_chunk, int64_t n_titles,
+                                                          int title_path, int sparse_path, float k_rrf, int k,
+                                                          float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+  extern __shared__ uint8_t smem_raw[];
+  SelectSmem* sm = reinterpret_cast<SelectSmem*>(smem_raw);
+  uint64_t* keys = sm->keys;
+  uint32_t* dropped = sm->hist;                    // bit per list position (kSortCap bits = 128 words)
+  const int q = blockIdx.x;
+  const int n_in = n_paths * depth;
+  const uint32_t np = max(next_pow2(static_cast<uint32_t>(n_in)), 2u);
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) dropped[i] = 0;
+  // sort entries by (id asc, position asc): descending sort of the complemented key
+  for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) {
+    uint64_t key = 0ull;
+    if (i < static_cast<uint32_t>(n_in)) {
+      const int p = i / depth, r = i - p * depth;
+      const int64_t o = p * path_stride + q * query_stride + r;
+      int64_t id = ids[o];
+      if (id >= 0 && p == title_path) id = (id < n_titles) ? title_to_chunk[id] : -1;
+      if (id >= 0 && p == sparse_path && !(scores[o] > 0.f)) id = -1;
+      if (id >= 0) key = ~((static_cast<uint64_t>(static_cast<uint32_t>(id)) << 32) | i);
+    }
+    keys[i] = key;
+  }
+  block_bitonic_desc(keys, np);
+  // a later entry with the same id in the same path is a duplicate (same-path entries of an id are adjacent)
+  for (uint32_t i = threadIdx.x + 1; i < np; i += blockDim.x) {
+    const uint64_t a = keys[i - 1], b = keys[i];
+    if (b != 0ull && a != 0ull && static_cast<uint32_t>((~a) >> 32) == static_cast<uint32_t>((~b) >> 32)) {
+      const uint32_t pa = static_cast<uint32_t>(~a), pb = static_cast<uint32_t>(~b);
+      if (pa / depth == pb / depth) atomicOr(&dropped[pb >> 5], 1u << (pb & 31));
+    }
+  }
+  __syncthreads();
+  // run heads sum their run sequentially = in (path, rank) order; rank = place among the kept entries of the path
+  uint64_t fused_key[(kSortCap + 255) / 256];
+  int n_mine = 0;
+  for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) {
+    const uint64_t key = keys[i];
+    uint64_t out = 0ull;
+    if (key != 0ull) {
+      const uint32_t id = static_cast<uint32_t>((~key) >> 32);
+      const bool head = (i == 0) || keys[i - 1] == 0ull || (static_cast<uint32_t>((~keys[i - 1]) >> 32) != id);
+      if (head) {
+        float s = 0.f;
+        for (uint32_t r = i; r < np && keys[r] != 0ull && static_cast<uint32_t>((~keys[r]) >> 32) == id; ++r) {
+          const uint32_t pos = static_cast<uint32_t>(~keys[r]);
+          if (dropped[pos >> 5] & (1u << (pos & 31))) continue;
+          const uint32_t p0 = (pos / depth) * depth;           // first position of this entry's path
+          uint32_t gone = 0;                                    // dropped entries of the path before this one
+          for (uint32_t wd = p0 >> 5; wd <= (pos >> 5); ++wd) {
+            uint32_t m = dropped[wd];
+            if (wd == (p0 >> 5)) m &= ~0u << (p0 & 31);
+            if (wd == (pos >> 5)) m &= (1u << (pos & 31)) - 1u;
+            gone += __popc(m);
+          }
+          const float rank = static_cast<float>(pos - p0 - gone + 1);
+          s = __fadd_rn(s, __fdiv_rn(1.0f, __fadd_rn(k_rrf, rank)));
+        }
+        out = make_key(s, id);
+      }
+    }
+    fused_key[n_mine++] = out;
+  }
+  __syncthreads();
+  n_mine = 0;
+  for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) keys[i] = fused_key[n_mine++];
+  block_bitonic_desc(keys, np);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const uint64_t key = (static_cast<uint32_t>(i) < np) ? keys[i] : 0ull;
+    const bool has = key != 0ull;
+    out_scores[static_cast<int64_t>(q) * k + i] = has ? key_score(key) : -3.402823466e+38f;
+    out_ids[static_cast<int64_t>(q) * k + i] = has ? static_cast<int64_t>(key_id(key)) : -1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// posting arrays checked on the device at vfi_bm25_create: flags[0] doc id out of range, flags[1] a posting list not
+// strictly ascending, flags[2] an impact <= 0 (or NaN) present
+// ------------------------------------------------------------------------------------------
+__global__ void bm25_validate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                     const float* __restrict__ data, int64_t n_vocab, int64_t nnz, int64_t n_docs,
+                                     uint32_t* __restrict__ flags) {
+  uint32_t bad_range = 0, bad_order = 0, non_pos = 0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nnz; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int32_t d = indices[i];
+    if (d < 0 || d >= n_docs) bad_range = 1;
+    if (!(data[i] > 0.f)) non_pos = 1;
+    if (i > 0 && indices[i - 1] >= d) {
+      // descending neighbours are fine only across a list boundary: is i the first posting of some token?
+      int64_t lo = 0, hi = n_vocab;             // largest t with indptr[t] <= i
+      while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (indptr[mid] <= i) lo = mid; else hi = mid - 1;
+      }
+      if (indptr[lo] != i) bad_order = 1;
+    }
+  }
+  if (bad_range) flags[0] = 1;
+  if (bad_order) flags[1] = 1;
+  if (non_pos) flags[2] = 1;
+}
+
+// rank-all helpers: (score, id) -> sortable pair, and back
+__global__ void rank_keys_kernel(const float* __restrict__ s, int64_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    keys[i] = ~float_orderable(s[i]);
+    vals[i] = static_cast<uint32_t>(i);
+  }
+}
+__global__ void ranked_out_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n, int64_t id_offset,
+                                  float* __restrict__ scores, int64_t* __restrict__ ids) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float sc = orderable_float(~keys[i]);
+    const int64_t id = static_cast<int64_t>(vals[i]) + id_offset;
+    scores[i] = sc;
+    ids[i] = id;
+  }
 }
 
 }  // namespace vfi

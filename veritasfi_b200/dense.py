@@ -98,17 +98,24 @@ class DenseIndex:
                                               N.MEM_DEVICE, _stream_ptr(self.device)))
         return ids, scores
 
-    def search_begin(self, q: torch.Tensor, k: int) -> "SearchTicket":
+    def search_begin(self, q: torch.Tensor, k: int, out=None) -> "SearchTicket":
         """Enqueue one batch (B <= 1024) and return at once; `search_finish(ticket)` waits, certifies and hands out
         (ids, scores).  Beginning batch i+1 before finishing batch i keeps the GPU busy while the host looks at the
-        certificate flag of batch i (vfi_index_search_begin / vfi_index_search_finish)."""
+        certificate flag of batch i (vfi_index_search_begin / vfi_index_search_finish).  out: optional contiguous
+        (ids int64 [B,k], scores float32 [B,k]) tensors to write into."""
         if not (isinstance(q, torch.Tensor) and q.is_cuda and q.dtype == torch.float32 and q.dim() == 2
                 and q.shape[1] == self.d and q.shape[0] > 0):
             raise ValueError("search_begin: need a non-empty float32 [B, d] cuda tensor")
         q = q.contiguous()
         B = q.shape[0]
-        ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
-        scores = torch.empty((B, k), dtype=torch.float32, device=self.device)
+        if out is None:
+            ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
+            scores = torch.empty((B, k), dtype=torch.float32, device=self.device)
+        else:
+            ids, scores = out
+            if not (ids.is_contiguous() and scores.is_contiguous() and ids.shape == (B, k) and scores.shape == (B, k)
+                    and ids.dtype == torch.int64 and scores.dtype == torch.float32):
+                raise ValueError("search_begin: out must be contiguous (int64 [B,k], float32 [B,k])")
         t = C.c_int(-1)
         N.check(N.load().vfi_index_search_begin(self._h, C.c_void_p(q.data_ptr()), B, int(k), C.c_void_p(scores.data_ptr()),
                                                 C.c_void_p(ids.data_ptr()), _stream_ptr(self.device), C.byref(t)))
@@ -117,6 +124,12 @@ class DenseIndex:
     def search_finish(self, ticket: "SearchTicket"):
         N.check(N.load().vfi_index_search_finish(self._h, ticket.ticket))
         return ticket.ids, ticket.scores
+
+    def ticket_flag_ptr(self, ticket: "SearchTicket") -> int:
+        """Device address of the batch's certificate counter (vfi_index_ticket_flag); valid until search_finish."""
+        p = C.c_void_p()
+        N.check(N.load().vfi_index_ticket_flag(self._h, ticket.ticket, C.byref(p)))
+        return p.value
 
     def search_host(self, q: np.ndarray, k: int):
         """Host in, host out (pinned or pageable numpy): the reference-facing call, copies included."""

@@ -98,7 +98,30 @@ class BM25Retriever:
         docs, scores = docs[0], scores[0]
         if self.min_score is not None:
             docs = [doc for doc, score in zip(docs, scores) if score >= self.min_score]
+        if isinstance(docs, bm25_compat.LazyRow):
+            # k beyond the eager head (the reference passes k = num_chunk and reads [:bm25_k], ensembleRetriever.py:189-190):
+            # the ids stay lazy too, so the ranks past the head are only produced if somebody reads them
+            return _LazyDocIds(docs), scores
         return [doc["id"] for doc in docs], scores
+
+
+class _LazyDocIds:
+    """`[doc["id"] for doc in docs]` of bm25Retriever.py:86 over a lazy row: evaluated on the part that is read."""
+
+    def __init__(self, docs):
+        self._docs = docs
+
+    def __len__(self):
+        return len(self._docs)
+
+    def __getitem__(self, key):
+        got = self._docs[key]
+        if isinstance(key, slice):
+            return [doc["id"] for doc in got]
+        return got["id"]
+
+    def __iter__(self):
+        return (doc["id"] for doc in self._docs)
 
 
 class EnsembleRetriever:

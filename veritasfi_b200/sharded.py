@@ -89,15 +89,21 @@ class PeerExchange:
             self.close(barrier=False)     # the all-reduce above already ordered every rank; nobody has pushed yet
             raise PeerExchangeUnavailable(str(err) if err is not None else "setup failed on another rank")
 
-    def merge(self, scores: torch.Tensor, ids: torch.Tensor, k_out: int):
+    def merge(self, scores: torch.Tensor, ids: torch.Tensor, k_out: int, fail_ptrs=(None, None), any_fail: torch.Tensor | None = None):
+        """fail_ptrs: up to two device addresses of certificate counters (DenseIndex.ticket_flag_ptr) of the searches that
+        produced these rows; any_fail: int32 [1] cuda tensor (zeroed by the caller) that every rank finds set to 1 when any
+        rank's rows were not final — see vfi_exchange_merge_flagged."""
         C, N = self._C, self._N
         B, k = scores.shape
         scores, ids = scores.contiguous(), ids.contiguous()
         out_s = torch.empty((B, k_out), dtype=torch.float32, device=self.device)
         out_i = torch.empty((B, k_out), dtype=torch.int64, device=self.device)
-        N.check(N.load().vfi_exchange_merge(self._h, C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()), B, k, int(k_out),
-                                            C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()),
-                                            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        fa, fb = (list(fail_ptrs) + [None, None])[:2]
+        N.check(N.load().vfi_exchange_merge_flagged(
+            self._h, C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()), B, k, int(k_out), C.c_void_p(out_s.data_ptr()),
+            C.c_void_p(out_i.data_ptr()), C.c_void_p(fa) if fa else None, C.c_void_p(fb) if fb else None,
+            C.c_void_p(any_fail.data_ptr()) if any_fail is not None else None,
+            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         return out_i, out_s
 
     def close(self, barrier: bool = True) -> None:
@@ -109,32 +115,102 @@ class PeerExchange:
             self._h = self._C.c_void_p()
 
 
+class ShardTicket:
+    """One sharded batch in flight (ShardedSearcher.search_begin)."""
+    __slots__ = ("local", "out", "slot", "event", "k")
+
+    def __init__(self, local, out, slot, event, k):
+        self.local, self.out, self.slot, self.event, self.k = local, out, slot, event, k
+
+
 class ShardedSearcher:
     """exchange + merge around any local searcher `local(q, k) -> (ids [B,k], scores [B,k])`.
 
     merge: callable (scores [G,B,k], ids [G,B,k], k) -> (ids [B,k], scores [B,k]); the CUDA merge kernel in
     production (veritasfi_b200.dense.merge_topk).  exchange: a PeerExchange (fused push + merge over NVLink peer
-    memory) or None (all-gather over the process group, then `merge`)."""
+    memory) or None (all-gather over the process group, then `merge`).  index: the DenseIndex behind `local` — enables
+    the pipelined form search_begin / search_finish (CUDA only)."""
 
-    def __init__(self, local: Callable, merge: Callable, group=None, exchange: "PeerExchange | None" = None):
+    def __init__(self, local: Callable, merge: Callable, group=None, exchange: "PeerExchange | None" = None, index=None):
         self.local = local
         self.merge = merge
         self.group = group
         self.exchange = exchange
+        self.index = index
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._flags_host = None     # pinned ring of "any rank repaired" flags, one per batch in flight
+        self._flags_dev = None
+        self._next_slot = 0
+        self.re_exchanges = 0
 
-    def search(self, q: torch.Tensor, k: int):
-        ids, scores = self.local(q, k)
+    def exchange_rows(self, scores: torch.Tensor, ids: torch.Tensor, k_out: int, fail_ptrs=(None, None), any_fail=None):
+        """Global top-k_out of every row over the ranks: scores/ids [R,k] per rank (global ids) -> (ids, scores) [R,k_out],
+        identical on all ranks.  Rows are independent, so the three lists of the hybrid retriever travel as R = 3*B rows."""
+        R, k = scores.shape
         if self.world == 1:
             return ids, scores
-        if self.exchange is not None and scores.shape[0] <= self.exchange.max_nq and k <= self.exchange.max_k:
-            return self.exchange.merge(scores, ids, k)
+        if self.exchange is not None and R <= self.exchange.max_nq and k <= self.exchange.max_k:
+            return self.exchange.merge(scores, ids, k_out, fail_ptrs, any_fail)
         mine = pack(scores, ids)
         flat = torch.empty((self.world * mine.shape[0], mine.shape[1]), dtype=mine.dtype, device=mine.device)
         dist.all_gather_into_tensor(flat, mine, group=self.group)     # rank-major concatenation along dim 0
         g_scores, g_ids = unpack(flat.view(self.world, mine.shape[0], mine.shape[1]), k)
-        return self.merge(g_scores, g_ids, k)
+        if any_fail is not None:      # the all-gather route: the ranks agree through one more (tiny) collective
+            mine_fail = torch.zeros(1, dtype=torch.int32, device=scores.device)
+            for p in fail_ptrs:
+                if p:
+                    mine_fail = torch.maximum(mine_fail, _int32_at(p, scores.device).clamp(max=1))
+            dist.all_reduce(mine_fail, op=dist.ReduceOp.MAX, group=self.group)
+            any_fail.copy_(mine_fail)
+        return self.merge(g_scores, g_ids, k_out)
+
+    def search(self, q: torch.Tensor, k: int):
+        ids, scores = self.local(q, k)
+        return self.exchange_rows(scores, ids, k)
+
+    # -- pipelined form: batch i+1 is enqueued (local search AND exchange) before the host looks at batch i ------------
+    def search_begin(self, q: torch.Tensor, k: int) -> ShardTicket:
+        """Enqueue the local search and, right behind it on the stream, the exchange of its (not yet certified) rows.  The
+        exchange carries this rank's certificate counter to every peer; search_finish repairs what failed and, if ANY rank
+        had to, all ranks exchange that batch once more — they agree on it without a host collective."""
+        if self.index is None:
+            raise RuntimeError("search_begin needs the DenseIndex behind the local searcher (make_sharded_dense)")
+        t = self.index.search_begin(q, k)
+        if self.world == 1:
+            return ShardTicket(t, None, -1, None, k)
+        dev = q.device
+        if self._flags_host is None:
+            self._flags_host = torch.zeros(64, dtype=torch.int32).pin_memory()
+            self._flags_dev = torch.zeros(64, dtype=torch.int32, device=dev)
+        slot = self._next_slot
+        self._next_slot = (slot + 1) % 64
+        any_fail = self._flags_dev[slot:slot + 1]
+        any_fail.zero_()
+        out = self.exchange_rows(t.scores, t.ids, k, (self.index.ticket_flag_ptr(t), None), any_fail)
+        self._flags_host[slot:slot + 1].copy_(any_fail, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return ShardTicket(t, out, slot, ev, k)
+
+    def search_finish(self, ticket: ShardTicket):
+        ids, scores = self.index.search_finish(ticket.local)     # waits for the local batch, repairs flagged queries
+        if self.world == 1:
+            return ids, scores
+        ticket.event.synchronize()
+        if int(self._flags_host[ticket.slot]) != 0:               # the same value on every rank
+            self.re_exchanges += 1
+            return self.exchange_rows(scores, ids, ticket.k)
+        return ticket.out
+
+
+def _int32_at(ptr: int, device) -> torch.Tensor:
+    """A [1] int32 cuda tensor aliasing a device address owned by libvfi (a certificate counter)."""
+    import ctypes as C
+
+    class _Arr:
+        __cuda_array_interface__ = {"shape": (1,), "typestr": "<i4", "data": (int(ptr), True), "version": 3}
+    return torch.as_tensor(_Arr(), device=device)
 
 
 def make_sharded_dense(index, group=None, exchange: str | None = None, max_nq: int = 1024, max_k: int = 256) -> ShardedSearcher:
@@ -159,4 +235,4 @@ def make_sharded_dense(index, group=None, exchange: str | None = None, max_nq: i
             import warnings
             warnings.warn(f"peer-memory exchange unavailable ({e}); using the NCCL all-gather route")
     return ShardedSearcher(lambda q, k: index.search_batch(q, k),
-                           lambda s, i, k: merge_topk(s, i, k), group, ex)
+                           lambda s, i, k: merge_topk(s, i, k), group, ex, index=index)
