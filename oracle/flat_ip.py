@@ -131,3 +131,52 @@ def search_faiss_like(xq, xb, k: int, block: int = 1024, threads: int | None = N
     I = np.full((nq, k), -1, np.int64)
     D[:, :kk], I[:, :kk] = run_s.numpy(), run_i.numpy()
     return D, I
+
+
+def search_blocks(xq, blocks, k: int, kc: int | None = None):
+    """`search` for a corpus that does not fit host memory at once (BASELINE configs 3 and 5): `blocks` yields
+    (first_row, rows fp32 [m,d]) in any order.  Per block an fp32 sgemm proposes kc candidates per query, which are rescored
+    canonically while the block is in memory; every row the block did NOT propose has an sgemm score <= the block's kc-th.
+    The result is the exact top-k iff the k-th exact score beats every block's bound + eps; a query that fails the test
+    raises (callers pick kc generously: this is a checker, not a product path)."""
+    import torch
+
+    xq = _f32c(xq)
+    nq, d = xq.shape
+    kc = kc or max(4 * k, k + 64)
+    tq = torch.from_numpy(xq)
+    qn = np.linalg.norm(xq.astype(np.float64), axis=1)
+    cand_s = [np.empty(0, np.float32) for _ in range(nq)]
+    cand_i = [np.empty(0, np.int64) for _ in range(nq)]
+    bound = np.full(nq, -np.inf)
+    xn2 = 0.0
+    for first, xb in blocks:
+        xb = _f32c(xb)
+        m = xb.shape[0]
+        xn2 = max(xn2, float((xb.astype(np.float64) ** 2).sum(1).max()))
+        s = tq @ torch.from_numpy(xb).T
+        kk = min(kc, m)
+        ts, ti = torch.topk(s, kk, dim=1)
+        ts, ti = ts.numpy(), ti.numpy()
+        for q in range(nq):
+            ex = canon_scores(xq[q], xb, ti[q])
+            cand_s[q] = np.concatenate([cand_s[q], ex])
+            cand_i[q] = np.concatenate([cand_i[q], ti[q] + first])
+            if kk < m:
+                bound[q] = max(bound[q], float(ts[q].min()))
+            if len(cand_s[q]) > 4 * kc:           # keep the running lists short
+                keep_s, keep_i = topk_pairs(cand_s[q], cand_i[q], kc)
+                cand_s[q], cand_i[q] = keep_s, keep_i
+    D, I = np.empty((nq, k), np.float32), np.empty((nq, k), np.int64)
+    xn = float(np.sqrt(xn2))
+    for q in range(nq):
+        n_have = len(cand_s[q])
+        ds, di = topk_pairs(cand_s[q], cand_i[q], min(k, n_have))
+        if n_have < k:
+            ds = np.concatenate([ds, np.full(k - n_have, -FLT_MAX, np.float32)])
+            di = np.concatenate([di, np.full(k - n_have, -1, np.int64)])
+        eps = 4.0 * d * 2.0 ** -24 * qn[q] * xn
+        if np.isfinite(bound[q]) and not (ds[k - 1] > bound[q] + eps):
+            raise RuntimeError(f"search_blocks: query {q} not certified with kc={kc}; raise kc")
+        D[q], I[q] = ds, di
+    return D, I

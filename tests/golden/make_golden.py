@@ -51,6 +51,23 @@ def main():
         json.dump(out, f, indent=1)
     print("wrote", len(out["cases"]), "cases;", sum(len(c["chunks"]) for c in out["cases"]), "chunks")
 
+    # BASELINE config C1 at its stated size (~10k chunks x 1024-d, 16 queries, top-10): the reference's EnsembleRetriever
+    # with k = 10 (`collections={'zeekr': 10}`, experiments/e2e/qa_e2e_async.py:67) and enable_expand as ragManager.py:104-114
+    # builds it, plus its FaissRetriever called with the 16 query strings as one batch.
+    world = fw.make_world_c1()
+    out = {"n_chunks": len(world["metas"]), "n_titles": len(world["titles"]), "cases": [], "faiss_batch": None}
+    with tempfile.TemporaryDirectory() as tmp:
+        write_bm25_dir(world, tmp)
+        chroma, ts = fw.make_collections(world)
+        r = EnsembleRetriever(tmp, chroma, ts, 10, fw.FakeEmbeddings(world), enable_expand=True)
+        for qi, (q, hyde) in enumerate(fw.QUERIES_C1):
+            out["cases"].append({"query": qi, "chunks": fw.summarize_light(r.invoke(q, list(hyde)))})
+        ids, dist = r.faiss_retriever.invoke([q for q, _ in fw.QUERIES_C1], 10)
+        out["faiss_batch"] = {"ids": [[int(i) for i in row] for row in ids], "scores": [[float(x).hex() for x in row] for row in dist]}
+    with open(os.path.join(HERE, "ensemble_golden_c1.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote C1:", len(out["cases"]), "cases;", sum(len(c["chunks"]) for c in out["cases"]), "chunks of", out["n_chunks"])
+
 
 if __name__ == "__main__":
     main()

@@ -225,3 +225,64 @@ def test_hybrid_fusion_kernel_equals_the_stagewise_oracle(torch_cuda, layout):
         ti, ts = ti.permute(1, 0, 2).contiguous(), ts.permute(1, 0, 2).contiguous()
     gi, gs = fuse_hybrid(ti, ts, torch.from_numpy(t2c).cuda(), 1, 2, k, 60.0, layout)
     assert (gi.cpu().numpy() == want_i).all() and (gs.cpu().numpy() == want_s).all()
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE sizes
+def test_full_size_c5_shard_equals_the_oracle(torch_cuda):
+    """One 1/8 shard of BASELINE config C5 (6.25M x 768 bf16, ONE query, top-10) on the streaming GEMV, equal to the CPU
+    oracle streaming the shard in 1M-row blocks; global ids through the shard's id offset."""
+    torch = torch_cuda
+    from oracle import flat_ip
+    from veritasfi_b200 import _native as N, synth
+    from veritasfi_b200.dense import DenseIndex
+    dev = torch.device("cuda", 0)
+    n, d, k, off = 6_250_000, 768, 10, 3 * 6_250_000
+    idx = DenseIndex(d, store="bf16", id_offset=off)
+    idx.reserve(n)
+    for c, r0 in enumerate(range(0, n, 1 << 20)):
+        idx.add(synth.dense_corpus_torch(min(1 << 20, n - r0), d, 900 + c, dev))
+    q = synth.dense_queries_torch(1, d, 901, dev)
+    ids, scores = idx.search_batch(q, k)
+    assert idx.stats().last_path == N.PATH_GEMV
+
+    def blocks():
+        for r0 in range(0, n, 1 << 20):
+            yield r0 + off, idx.read_rows(r0, min(1 << 20, n - r0))
+    D0, I0 = flat_ip.search_blocks(q.cpu().numpy(), blocks(), k, kc=64)
+    assert (ids.cpu().numpy() == I0).all() and (scores.cpu().numpy() == D0).all()
+    idx.close()
+
+
+def test_full_size_c4_shard_bm25_and_fusion_equal_the_oracle(torch_cuda):
+    """One 1/8 shard of BASELINE config C4 (625k docs, V = 262144, ~96 unique terms per doc, 6e7 postings built on the
+    GPU): BM25 top-200 for 16 queries and the fused top-50 equal to the CPU oracle."""
+    torch = torch_cuda
+    from oracle import bm25 as obm, fusion as ofu
+    from veritasfi_b200 import synth
+    from veritasfi_b200.bm25_compat import GpuPostings
+    from veritasfi_b200.multipath import fuse_hybrid
+    dev = torch.device("cuda", 0)
+    n, V, L, k, B = 625_000, 262_144, 200, 50, 16
+    tok, doc, tf, dl = synth.zipf_postings_torch(n, V, 1001, dev, mean_len=128)
+    df = torch.bincount(tok, minlength=V)
+    avgdl = float(dl.sum()) / n
+    indptr, indices, data = synth.bm25_impacts_torch(tok, doc, tf, dl, V, n, df, avgdl)
+    assert 5.5e7 < indices.numel() < 6.5e7
+    gp = GpuPostings.from_device(indptr, indices, data, n)
+    qs = synth.bm25_queries(B, V, 1001)
+    bi, bs = gp.search(qs, L)
+    csc = (indptr.cpu().numpy(), indices.cpu().numpy(), data.cpu().numpy())
+    oi, os_ = obm.retrieve(*csc, qs, n, L)
+    assert (bi == oi).all() and (bs == os_).all()
+    # fusion at the C4 list shapes: two synthetic dense lists + the BM25 list
+    rng = np.random.default_rng(12)
+    t2c = rng.integers(0, n, size=125_000).astype(np.int64)
+    i0 = np.stack([rng.permutation(n)[:L] for _ in range(B)]).astype(np.int64)
+    it = np.stack([rng.permutation(125_000)[:L] for _ in range(B)]).astype(np.int64)
+    sc = np.sort(rng.random((B, L)).astype(np.float32), axis=1)[:, ::-1].copy()
+    ids = np.stack([i0, it, oi], axis=1)
+    scores = np.stack([sc, sc, os_], axis=1)
+    want_i, want_s = ofu.hybrid(ids, scores, t2c, 1, 2, 60.0, k)
+    gi, gs = fuse_hybrid(torch.from_numpy(ids).cuda(), torch.from_numpy(scores).cuda(), torch.from_numpy(t2c).cuda(), 1, 2, k, 60.0, "bpl")
+    assert (gi.cpu().numpy() == want_i).all() and (gs.cpu().numpy() == want_s).all()
+    gp.close()

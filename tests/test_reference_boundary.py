@@ -5,8 +5,12 @@
   * CPU             the host-side mirror (veritasfi_b200.retrievers) reproduces it with oracle doubles injected
                     where the CUDA library would be called — this checks the orchestration logic only;
   * GPU             the mirror on the real kernels reproduces it, and so do the unmodified reference files once
-                    veritasfi_b200.dropin.install() has put our faiss/bm25s modules in place (build container only:
-                    /root/reference does not exist on the GPU box)."""
+                    veritasfi_b200.dropin.install() has put our faiss/bm25s modules in place.  /root/reference does not
+                    exist on the GPU box: there the test imports the byte-identical copies that __graft_entry__.build()
+                    staged under oracle/_ref/reference_src (git-ignored), after checking their SHA-256 against
+                    tests/golden/reference_sha256.json.
+  * C1              the same at BASELINE config C1's stated size (tests/golden/ensemble_golden_c1.json: ~10.9k chunks x
+                    1024-d, 16 queries, top-10), where the reference's calls reach the streaming and tensor-core kernels."""
 import json
 import os
 import sys
@@ -17,7 +21,25 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import fixture_world as fw  # noqa: E402
 import oracle_doubles as od  # noqa: E402
 
-REFERENCE = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGED = os.path.join(ROOT, "oracle", "_ref", "reference_src")
+
+
+def _reference_dir():
+    """The reference tree (build container) or its staged, hash-checked copy (GPU box); None when neither exists."""
+    if os.path.isdir("/root/reference/src/utils"):
+        return "/root/reference"
+    if os.path.isdir(os.path.join(STAGED, "src", "utils")):
+        import hashlib
+        want = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_sha256.json")))["sha256"]
+        for rel, digest in want.items():
+            path = os.path.join(STAGED, rel)
+            assert hashlib.sha256(open(path, "rb").read()).hexdigest() == digest, f"staged {rel} is not the reference's file"
+        return STAGED
+    return None
+
+
+REFERENCE = _reference_dir()
 CONFIGS = [dict(k=5, enable_expand=True), dict(k=3, faiss_k=6, bm25_k=4, faiss_ts_k=2, enable_expand=False),
            dict(k=4, faiss_k=0, bm25_k=5, faiss_ts_k=3, enable_expand=True)]
 
@@ -79,7 +101,7 @@ def test_mirror_replaces_metadata_scans_with_maps_but_keeps_fetch_pattern(tmp_pa
         r.bm25_retriever.invoke("x", 3, metadata_filters={"a": 1})
 
 
-@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference tree only exists in the build container")
+@pytest.mark.skipif(REFERENCE is None, reason="neither /root/reference nor its staged copy is present")
 def test_committed_golden_is_what_the_unmodified_reference_produces(tmp_path):
     for name in [m for m in sys.modules if m == "src" or m.startswith("src.")]:
         del sys.modules[name]
@@ -107,18 +129,77 @@ def test_mirror_on_the_gpu_kernels_reproduces_the_reference(tmp_path):
     _assert_equal_to_golden(_run(retrievers.EnsembleRetriever, str(tmp_path), world))
 
 
+def _purge_src_modules():
+    for name in [m for m in sys.modules if m == "src" or m.startswith("src.")]:
+        del sys.modules[name]
+
+
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference tree only exists in the build container")
 def test_unmodified_reference_files_on_the_gpu_kernels(tmp_path):
+    """The reference's own retriever files, byte for byte, on the CUDA kernels: mini world and C1 world."""
+    assert REFERENCE is not None, "run __graft_entry__.build() where /root/reference exists: it stages the files for the GPU box"
     from veritasfi_b200 import dropin
-    od.install_reference_shims()      # langchain_* stubs
-    dropin.install(override_stemmer=True)   # faiss / bm25s / Stemmer -> this package
+    _purge_src_modules()
+    od.install_reference_shims(langchain_only=True)      # langchain_* stubs only
+    dropin.install(override_stemmer=True)                # faiss / bm25s / Stemmer -> this package
     sys.path.insert(0, REFERENCE)
     try:
         from src.utils.ensembleRetriever import EnsembleRetriever
+        import faiss
+        assert faiss.IndexFlatIP.__module__ == "veritasfi_b200.faiss_compat"
         world = fw.make_world()
-        od.write_bm25_dir(world, str(tmp_path))
-        _assert_equal_to_golden(_run(EnsembleRetriever, str(tmp_path), world))
+        od.write_bm25_dir(world, str(tmp_path / "mini"))
+        _assert_equal_to_golden(_run(EnsembleRetriever, str(tmp_path / "mini"), world))
+        _assert_c1(EnsembleRetriever, str(tmp_path / "c1"), check_paths=True)
     finally:
         sys.path.remove(REFERENCE)
         dropin.uninstall()
+        _purge_src_modules()
+
+
+# ---- BASELINE config C1 at its stated size -------------------------------------------------------------------------
+_C1 = {}
+
+
+def _c1_world():
+    if "world" not in _C1:
+        _C1["world"] = fw.make_world_c1()
+    return _C1["world"]
+
+
+def _assert_c1(cls, tmp, check_paths=False):
+    world = _c1_world()
+    gold = fw.load_golden("ensemble_golden_c1.json")
+    assert gold["n_chunks"] == len(world["metas"]) and gold["n_titles"] == len(world["titles"])
+    od.write_bm25_dir(world, tmp)
+    chroma, ts = fw.make_collections(world)
+    r = cls(tmp, chroma, ts, 10, fw.FakeEmbeddings(world), enable_expand=True)
+    for case in gold["cases"]:
+        q, hyde = fw.QUERIES_C1[case["query"]]
+        assert fw.summarize_light(r.invoke(q, list(hyde))) == case["chunks"], f"C1 query {case['query']}"
+    if check_paths:
+        from veritasfi_b200 import _native as N
+        # the depth-2048 chunk search of the last invoke ran on the exact streaming scorer, its title search on the GEMV
+        assert r.faiss_retriever.index.stats().last_path == N.PATH_EXACT
+        assert r.title_summary_faiss_retriever.index.stats().last_path == N.PATH_GEMV
+    ids, dist = r.faiss_retriever.invoke([q for q, _ in fw.QUERIES_C1], 10)        # 16 queries, top-10: the C1 batch
+    assert [[int(i) for i in row] for row in ids] == gold["faiss_batch"]["ids"]
+    assert [[float(x).hex() for x in row] for row in dist] == gold["faiss_batch"]["scores"]
+    if check_paths:
+        assert r.faiss_retriever.index.stats().last_path == N.PATH_FUSED               # the tcgen05 kernel
+
+
+def test_c1_mirror_with_oracle_doubles_reproduces_the_reference(tmp_path, monkeypatch):
+    from veritasfi_b200 import retrievers
+    monkeypatch.setattr(retrievers.faiss_compat, "IndexFlatIP", od.OracleIndexFlatIP)
+    monkeypatch.setattr(retrievers.faiss_compat, "normalize_L2", od.oracle_normalize_L2)
+    monkeypatch.setattr(retrievers.bm25_compat, "BM25", od.OracleBM25)
+    monkeypatch.setattr(retrievers.bm25_compat, "tokenize", od.oracle_tokenize)
+    monkeypatch.setattr(retrievers, "make_stemmer", lambda lang="english": od.OracleStemmer())
+    _assert_c1(retrievers.EnsembleRetriever, str(tmp_path))
+
+
+@pytest.mark.gpu
+def test_c1_mirror_on_the_gpu_kernels_reproduces_the_reference(tmp_path):
+    from veritasfi_b200 import retrievers
+    _assert_c1(retrievers.EnsembleRetriever, str(tmp_path), check_paths=True)

@@ -50,6 +50,18 @@ def main():
             print(f"[multi-gpu G={world} n={n} d={d} nq={nq} k={k}] all ranks equal to unsharded oracle: {bool(flag.item())}", flush=True)
         ok &= bool(flag.item())
         idx.close()
+    # the pipelined sharded searcher (exchange enqueued behind the local search, agreement on re-exchange through the
+    # exchange itself) and the sharded hybrid retriever (chunk rows, title rows, BM25 doc ranges; one packed exchange;
+    # fusion after the merge) against the CPU oracle, on both exchange routes
+    import bench
+    ctx = bench.Ctx()
+    ctx.rank, ctx.world, ctx.local_rank, ctx.dev = rank, world, local, dev
+    for mode in ("peer", "nccl"):
+        for fn in (bench.parity_small_dense, bench.parity_small_hybrid):
+            res = fn(ctx, mode)
+            if rank == 0:
+                print(f"[multi-gpu G={world} {fn.__name__} exchange={mode}] {res['what']}: {bool(res['ok'])}", flush=True)
+            ok &= bool(res["ok"])
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

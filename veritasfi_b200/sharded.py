@@ -236,3 +236,23 @@ def make_sharded_dense(index, group=None, exchange: str | None = None, max_nq: i
             warnings.warn(f"peer-memory exchange unavailable ({e}); using the NCCL all-gather route")
     return ShardedSearcher(lambda q, k: index.search_batch(q, k),
                            lambda s, i, k: merge_topk(s, i, k), group, ex, index=index)
+
+
+def make_row_exchange(device, exchange: str | None = None, max_rows: int = 3072, max_k: int = 256, group=None) -> ShardedSearcher:
+    """The exchange half alone (`exchange_rows`) for callers that produce their per-rank rows themselves — the hybrid
+    retriever sends the lists of its three paths as 3*B rows in one exchange."""
+    import os
+
+    from .dense import merge_topk
+
+    mode = (exchange or os.environ.get("VFI_EXCHANGE", "peer")).lower()
+    if mode not in ("peer", "nccl"):
+        raise ValueError("exchange must be 'peer' or 'nccl'")
+    ex = None
+    if mode == "peer" and dist.is_initialized() and dist.get_world_size(group) > 1:
+        try:
+            ex = PeerExchange(torch.device(device), max_rows, max_k, group)
+        except PeerExchangeUnavailable as e:
+            import warnings
+            warnings.warn(f"peer-memory exchange unavailable ({e}); using the NCCL all-gather route")
+    return ShardedSearcher(None, lambda s, i, k: merge_topk(s, i, k), group, ex)

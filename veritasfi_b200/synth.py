@@ -104,3 +104,51 @@ def bm25_queries(b: int, n_vocab: int, seed: int, tmin: int = 4, tmax: int = 16,
         pick = rng.random(t) < 0.5
         out.append(np.where(pick, z, uni).astype(np.int32).tolist())
     return out
+
+
+def zipf_postings_torch(n_docs: int, n_vocab: int, seed: int, device, mean_len: int = 128, s: float = 1.1, doc_chunk: int = 1 << 20):
+    """The same synthetic postings generated on the GPU for one doc shard (BASELINE configs[3] is 5 M docs, 6.4e8 tokens:
+    too slow to build with numpy).  Returns token-major COUNTS, not impacts: (tok int64 [nnz], doc int64 [nnz] ascending per
+    token, tf int64 [nnz], dl int64 [n_docs]) — impacts need the GLOBAL df and avgdl (`bm25_impacts_torch`)."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    ranks = torch.arange(1, n_vocab + 1, dtype=torch.float64, device=device)
+    cdf = torch.cumsum(ranks.pow(-s) / ranks.pow(-s).sum(), dim=0)
+    dl_all, keys = [], []
+    for d0 in range(0, n_docs, doc_chunk):
+        nd = min(doc_chunk, n_docs - d0)
+        dl = torch.poisson(torch.full((nd,), float(mean_len), device=device), generator=g).clamp_min(1).long()
+        total = int(dl.sum())
+        u = torch.rand(total, generator=g, device=device, dtype=torch.float64)
+        tok = torch.searchsorted(cdf, u).clamp_max(n_vocab - 1)
+        doc = torch.repeat_interleave(torch.arange(d0, d0 + nd, device=device), dl)
+        k = torch.unique(tok * n_docs + doc, return_counts=True)     # (token, doc) pairs of this chunk with their tf
+        keys.append(k)
+        dl_all.append(dl)
+        del u, tok, doc
+    key = torch.cat([k[0] for k in keys])
+    tf = torch.cat([k[1] for k in keys])
+    del keys
+    key, order = torch.sort(key)                                       # token-major, doc ascending
+    tf = tf[order]
+    del order
+    tok = key // n_docs
+    doc = key - tok * n_docs
+    return tok, doc, tf, torch.cat(dl_all)
+
+
+def bm25_impacts_torch(tok, doc, tf, dl, n_vocab: int, n_docs_total: int, df_global, avgdl: float, k1: float = 1.5, b: float = 0.75):
+    """bm25s-lucene impacts (the formula of bm25_compat.build_csc) for one doc shard on the GPU, from GLOBAL document
+    frequencies and average length.  Returns (indptr int64 [V+1], indices int32 [nnz], data float32 [nnz]) cuda tensors."""
+    import torch
+
+    df = df_global.double()
+    idf = torch.log(1.0 + (n_docs_total - df + 0.5) / (df + 0.5))
+    tfd = tf.double()
+    tfc = tfd / (tfd + k1 * (1.0 - b + b * dl[doc].double() / (avgdl if avgdl > 0 else 1.0)))
+    data = (idf[tok] * tfc).float()
+    indptr = torch.zeros(n_vocab + 1, dtype=torch.int64, device=tok.device)
+    indptr[1:] = torch.cumsum(torch.bincount(tok, minlength=n_vocab), dim=0)
+    return indptr, doc.int(), data
