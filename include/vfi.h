@@ -129,8 +129,10 @@ enum {
   VFI_OPT_TAU_HINT = 4,      /* 1 (default): estimate a per-query admission threshold from a row sample (chunk maxima); 0: off;
                                 2: debug, admit nothing; 3: as 1 from every sampled score */
   VFI_OPT_NUM_CTAS = 5,      /* 0 = one CTA per SM */
-  VFI_OPT_CTA_PAIR = 7       /* tcgen05 cta_group::2 kernel (two SMs share every corpus tile; a batch with an odd number of
+  VFI_OPT_CTA_PAIR = 7,      /* tcgen05 cta_group::2 kernel (two SMs share every corpus tile; a batch with an odd number of
                                 128-query tiles gets a padding tile): 0 auto = on, 1 off (single-CTA kernel), 2 on */
+  VFI_OPT_TAU_M = 9          /* admission hint = the m-th best score of a row sample: 0 auto (8 for large shards; 16 or 32 with a
+                                denser sample when k'/N is large and passing rows would swamp the epilogue), or 8 / 16 / 32 */
 };
 int vfi_index_set_option(vfi_index_t* idx, int opt, int64_t value);
 

@@ -163,7 +163,7 @@ struct vfi_index {
   DevBuf stage;            // add()/read_rows staging (writer lock / own lock)
   std::mutex stage_mu;
   // options (written under the writer lock)
-  int64_t opt_overfetch = 0, opt_force_path = 0, opt_profile = 0, opt_tau_hint = 1, opt_num_ctas = 0, opt_cta_pair = 0;
+  int64_t opt_overfetch = 0, opt_force_path = 0, opt_profile = 0, opt_tau_hint = 1, opt_num_ctas = 0, opt_cta_pair = 0, opt_tau_m = 0;
   std::shared_mutex rw;    // searches share it, add/reserve/options own it
   std::mutex pool_mu;      // workspace pool, tickets, stats
   std::vector<std::unique_ptr<Workspace>> pool;
@@ -401,6 +401,10 @@ int vfi_index_set_option(vfi_index_t* idx, int opt, int64_t value) {
     case VFI_OPT_PROFILE: idx->opt_profile = value; break;
     case VFI_OPT_TAU_HINT: idx->opt_tau_hint = value; break;
     case VFI_OPT_NUM_CTAS: idx->opt_num_ctas = value; break;
+    case VFI_OPT_TAU_M:
+      if (value != 0 && value != 8 && value != 16 && value != 32) return fail(VFI_ERR_INVALID, "VFI_OPT_TAU_M: 0 auto, 8, 16 or 32");
+      idx->opt_tau_m = value;
+      break;
     case VFI_OPT_CTA_PAIR:
       if (value < 0 || value > 2) return fail(VFI_ERR_INVALID, "VFI_OPT_CTA_PAIR: 0 auto, 1 off, 2 on");
       idx->opt_cta_pair = value;
@@ -660,20 +664,37 @@ int search_launch(vfi_index* idx, Workspace* ws, const float* q_dev, int nq, int
   int n_groups = 0, nq_pad = 0, cap = 0;
   const float* tau = nullptr;
   if (path == 2 && idx->opt_tau_hint != 0 && !no_hint) {
-    // admission hint: the m-th best score of a strided row sample estimates a threshold that about
-    // 16k' rows of the shard exceed.  It only prunes work; exactness is re-established below.
-    // Sample every s-th row with s = 2k'+1.  tau = the m-th best sampled score with m = 8: about
-    // m*s = 16k' rows of the shard are expected above it, and fewer than k' with probability
-    // P(Gamma(8) < 1/2) ~ 1e-7 per query (then the batch is simply redone without the hint).
-    const int m = 8;
-    const int64_t rs = 2 * static_cast<int64_t>(keep) + 1;
+    // Admission hint: tau = the m-th best score of a strided row sample (every s-th row).  The rows of the shard above tau
+    // number m sampled ones plus a NegBinomial(m, 1/s) count of unsampled ones; (m, s) pairs are chosen so that fewer than
+    // k' rows pass with probability <= 1e-7 per query (then the batch is simply redone without the hint).  The hint only
+    // prunes work; exactness is re-established below.
+    //   m = 8,  s = 2k'+1   : ~16 k' rows pass, the sample is 1/(2k') of the shard        (large shards: C2, C3)
+    //   m = 16, s = 0.34 k' : ~5.5 k' rows pass, sample 3/k'                               (N/k' of a few thousand)
+    //   m = 32, s = k'/10   : ~3.2 k' rows pass, sample 10/k'                              (small shards, deep lists: the
+    //                         title path of the hybrid retriever, 125k rows at k' = 256)
+    // A passing row costs epilogue instructions (32 queries share a warp, so a warp takes the slow branch of a 4-column
+    // group with probability ~128 f, f = passing fraction): at f = 3 % the epilogue, not the tensor pipe, bounds K1
+    // (measured: 0.43 of peak on the title path with m = 8).  The denser sample is the cheaper evil there.
+    int m = 8;
+    int64_t rs = 2 * static_cast<int64_t>(keep) + 1;
+    {
+      const double f8 = 16.0 * keep / static_cast<double>(n);
+      const int64_t s16 = std::max<int64_t>(2, static_cast<int64_t>(0.34 * keep));
+      const int64_t s32 = std::max<int64_t>(2, keep / 10);
+      int want = 8;
+      if (f8 > 0.0025) want = (16.0 * s16 / static_cast<double>(n) > 0.0025 && s32 >= 12) ? 32 : 16;
+      if (idx->opt_tau_m == 8 || idx->opt_tau_m == 16 || idx->opt_tau_m == 32) want = static_cast<int>(idx->opt_tau_m);
+      if (want == 16) { m = 16; rs = s16; }
+      if (want == 32) { m = 32; rs = s32; }
+    }
     const int64_t rr = n / rs;
     if (rr >= 4 * m || idx->opt_tau_hint == 2) {
       // The sample pass keeps one value per (query, 32 sampled rows) — the chunk's largest tensor-core score — instead of
       // every score: the m-th largest chunk maximum is at most the m-th largest sampled score (equal unless two of the
       // best m samples share a chunk), so it is a valid, marginally looser hint, and the threshold kernel reads 32 x less.
       // VFI_OPT_TAU_HINT = 3 keeps the full sample (every score stored) for comparison.
-      const bool full = idx->opt_tau_hint == 3;
+      // (with few sampled rows per query the chunk maxima collide: every score is kept instead)
+      const bool full = idx->opt_tau_hint == 3 || ceil_div(rr, 32) < 8 * m;
       const int64_t ld = full ? ceil_div(rr, vfi::kBN) * vfi::kBN : ceil_div(rr, vfi::kBN) * (vfi::kBN / 32);
       const int64_t n_vals = full ? rr : ceil_div(rr, 32);
       const int64_t nq_pad_s = round_up(ceil_div(nq, vfi::kBM), 2) * vfi::kBM;

@@ -342,6 +342,10 @@ __global__ void keys_to_scores_kernel(const uint64_t* __restrict__ keys, int64_t
 // completion on a per-warp mbarrier) straight into its own padded shared-memory row: no LSU load instruction, no register
 // staging, no transposition.  One stage per warp; the other resident warps (20 per SM) hide the copy.  The query is
 // widened to fp64 once per CTA.  Floor: the HBM read of the candidate rows, nq * k' * d * sizeof(RowT) bytes.
+// Round 2 tried two candidates per thread with alternating pieces (the copy of one in flight while the other is summed):
+// 104 us instead of 77 us at 1024 x 128 rows and 49 us instead of 35 us at 256 queries (ncu: 3.4 warps per SM active, stalls on
+// the dependent DFMA chain) — halving the threads doubles every thread's serial fp64 chain, and the kernel is bound by
+// per-CTA latency x waves, not by bytes.  profiles/r2_ncu_summary.md has the capture.
 // ------------------------------------------------------------------------------------------
 constexpr int kRfMaxDp = 4096;          // query held as fp64 in shared memory (32 KB at the limit)
 template <int PIECE>
