@@ -386,6 +386,7 @@ def run_dense(args, name, w, ctx, config, steps, warmup, result_out):
     index.set_option(N.OPT_PROFILE, 1)
     if args.pair is not None:
         index.set_option(N.OPT_CTA_PAIR, args.pair)
+    index.set_option(N.OPT_TAU_M, args.tau_m)
     searcher = make_sharded_dense(index, exchange=args.exchange, max_nq=w["b"], max_k=w["k"])
     q_dev = synth.dense_queries_torch(w["b"], w["d"], SEED, ctx.dev)
     n_buf = 3
@@ -784,6 +785,7 @@ def main():
     ap.add_argument("--no-full-cpu-step", action="store_true", help="reference arm: skip the one full-corpus step")
     ap.add_argument("--hint", type=int, default=1)
     ap.add_argument("--pair", type=int, default=None, help="VFI_OPT_CTA_PAIR (1 = single-CTA kernel, for comparison)")
+    ap.add_argument("--tau-m", type=int, default=0, help="VFI_OPT_TAU_M (0 auto, 8/16/32: admission hint = m-th best of a row sample)")
     ap.add_argument("--sync", action="store_true", help="one synchronous search (+ exchange) per step instead of two batches in flight")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: fused peer-memory push+merge kernel over NVLink, or NCCL all-gather + merge kernel")

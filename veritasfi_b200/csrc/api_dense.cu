@@ -668,13 +668,16 @@ int search_launch(vfi_index* idx, Workspace* ws, const float* q_dev, int nq, int
     // number m sampled ones plus a NegBinomial(m, 1/s) count of unsampled ones; (m, s) pairs are chosen so that fewer than
     // k' rows pass with probability <= 1e-7 per query (then the batch is simply redone without the hint).  The hint only
     // prunes work; exactness is re-established below.
-    //   m = 8,  s = 2k'+1   : ~16 k' rows pass, the sample is 1/(2k') of the shard        (large shards: C2, C3)
-    //   m = 16, s = 0.34 k' : ~5.5 k' rows pass, sample 3/k'                               (N/k' of a few thousand)
+    //   m = 8,  s = 2k'+1   : ~16 k' rows pass, the sample is 1/(2k') of the shard        (C3 on 1-2 GPUs)
+    //   m = 16, s = 0.34 k' : ~5.5 k' rows pass, sample 3/k'                               (C2; C3 shards on 4-8 GPUs; the
+    //                                                                                        chunk path of the hybrid)
     //   m = 32, s = k'/10   : ~3.2 k' rows pass, sample 10/k'                              (small shards, deep lists: the
     //                         title path of the hybrid retriever, 125k rows at k' = 256)
     // A passing row costs epilogue instructions (32 queries share a warp, so a warp takes the slow branch of a 4-column
-    // group with probability ~128 f, f = passing fraction): at f = 3 % the epilogue, not the tensor pipe, bounds K1
-    // (measured: 0.43 of peak on the title path with m = 8).  The denser sample is the cheaper evil there.
+    // group with probability ~128 f, f = passing fraction).  Measured on B200: K1 gets 5.5 % faster when f falls from
+    // 0.16 % to 0.06 % (a 1/8 shard of C3: 2.05 -> 1.93 ms, 0.93 -> 0.98 of peak) and 5 % at C2; at f = 3 % the epilogue,
+    // not the tensor pipe, bounds K1 (0.43 of peak on the title path with m = 8, 0.79 with m = 32).  The denser sample costs
+    // 1/s of a K1 pass, so it pays when f8 = 16k'/N exceeds ~0.06 % (m = 16) / ~0.75 % (m = 32).
     int m = 8;
     int64_t rs = 2 * static_cast<int64_t>(keep) + 1;
     {
@@ -682,7 +685,8 @@ int search_launch(vfi_index* idx, Workspace* ws, const float* q_dev, int nq, int
       const int64_t s16 = std::max<int64_t>(2, static_cast<int64_t>(0.34 * keep));
       const int64_t s32 = std::max<int64_t>(2, keep / 10);
       int want = 8;
-      if (f8 > 0.0025) want = (16.0 * s16 / static_cast<double>(n) > 0.0025 && s32 >= 12) ? 32 : 16;
+      if (f8 > 0.0075 && s32 >= 12) want = 32;
+      else if (f8 > 0.0006) want = 16;
       if (idx->opt_tau_m == 8 || idx->opt_tau_m == 16 || idx->opt_tau_m == 32) want = static_cast<int>(idx->opt_tau_m);
       if (want == 16) { m = 16; rs = s16; }
       if (want == 32) { m = 32; rs = s32; }

@@ -136,8 +136,8 @@ struct vfi_bm25 {
   int64_t n_vocab = 0, n_docs = 0, nnz = 0, id_offset = 0;
   int all_positive = 1;
   int64_t* indptr = nullptr;
-  int32_t* indices = nullptr;
-  float* data = nullptr;
+  int32_t* indices = nullptr;     // doc ids: range-boundary searches
+  uint2* packed = nullptr;        // {byte offset in the range accumulator, impact}: what the scoring loop streams
   std::vector<int64_t> h_indptr;  // host copy: df lookups for stats and validation
   int profile = 0;
   vfi_bm25_stats stats{};
@@ -205,15 +205,26 @@ int bm25_create_impl(const int64_t* indptr, const int32_t* indices, const float*
   if (b->h_indptr[0] != 0 || nnz < 0 || (nnz > 0 && (!indices || !data))) return bail(fail(VFI_ERR_INVALID, "bad posting arrays"));
   for (int64_t t = 0; t < n_vocab; ++t)
     if (b->h_indptr[t] > b->h_indptr[t + 1]) return bail(fail(VFI_ERR_INVALID, "indptr must be non-decreasing"));
+  static_assert((vfi::kBmRange & (vfi::kBmRange - 1)) == 0, "packed postings need a power-of-two range");
+  float* d_data = nullptr;        // the impacts as given: validated, packed, then released
+  const float* data_dev = data;
   if (cudaMalloc(&b->indptr, sizeof(int64_t) * (n_vocab + 1)) != cudaSuccess ||
       cudaMalloc(&b->indices, std::max<size_t>(16, sizeof(int32_t) * nnz)) != cudaSuccess ||
-      cudaMalloc(&b->data, std::max<size_t>(16, sizeof(float) * nnz)) != cudaSuccess)
+      cudaMalloc(&b->packed, std::max<size_t>(16, sizeof(uint2) * nnz)) != cudaSuccess ||
+      (mem == VFI_MEM_HOST && cudaMalloc(&d_data, std::max<size_t>(16, sizeof(float) * nnz)) != cudaSuccess))
     return bail(fail(VFI_ERR_NOMEM, "cudaMalloc postings failed"));
+  struct FreeData {
+    float* p;
+    ~FreeData() { if (p) cudaFree(p); }
+  } free_data{d_data};
   const cudaMemcpyKind kind = mem == VFI_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   cudaMemcpy(b->indptr, b->h_indptr.data(), sizeof(int64_t) * (n_vocab + 1), cudaMemcpyHostToDevice);
   if (nnz > 0) {
     cudaMemcpy(b->indices, indices, sizeof(int32_t) * nnz, kind);
-    cudaMemcpy(b->data, data, sizeof(float) * nnz, kind);
+    if (mem == VFI_MEM_HOST) {
+      cudaMemcpy(d_data, data, sizeof(float) * nnz, kind);
+      data_dev = d_data;
+    }
   }
   // The kernel indexes its shared accumulator with the doc ids: every posting list must hold in-range, strictly
   // ascending doc ids (the bm25s layout).  Checked on the device, which also finds whether every impact is positive.
@@ -222,7 +233,9 @@ int bm25_create_impl(const int64_t* indptr, const int32_t* indices, const float*
   cudaMemset(d_flags, 0, 16);
   if (nnz > 0) {
     const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div(nnz, 256), 148 * 32));
-    vfi::bm25_validate_kernel<<<blocks, 256>>>(b->indptr, b->indices, b->data, n_vocab, nnz, n_docs, d_flags);
+    vfi::bm25_validate_kernel<<<blocks, 256>>>(b->indptr, b->indices, data_dev, n_vocab, nnz, n_docs, d_flags);
+    vfi::bm25_pack_kernel<<<blocks, 256>>>(b->indices, data_dev, nnz, b->packed);
+    LAUNCHED();
     LAUNCHED();
   }
   uint32_t h_flags[4] = {0, 0, 0, 0};
@@ -258,7 +271,7 @@ int vfi_bm25_destroy(vfi_bm25_t* b) {
   cudaDeviceSynchronize();
   if (b->indptr) cudaFree(b->indptr);
   if (b->indices) cudaFree(b->indices);
-  if (b->data) cudaFree(b->data);
+  if (b->packed) cudaFree(b->packed);
   for (BmScratch* s : b->pool) {
     s->destroy();
     delete s;
@@ -366,7 +379,7 @@ int vfi_bm25_search(vfi_bm25_t* b, const int32_t* q_tokens, const int64_t* q_ind
     vfi::Bm25Params p{};
     p.indptr = b->indptr;
     p.indices = b->indices;
-    p.data = b->data;
+    p.packed = b->packed;
     p.n_docs = b->n_docs;
     p.n_seg = static_cast<int>(n_seg);
     p.seg_docs = seg_docs;
@@ -453,7 +466,7 @@ static int bm25_dump_scores(vfi_bm25* b, BmScratch* w, const int32_t* q_tokens, 
   vfi::Bm25Params p{};
   p.indptr = b->indptr;
   p.indices = b->indices;
-  p.data = b->data;
+  p.packed = b->packed;
   p.n_docs = b->n_docs;
   p.n_seg = static_cast<int>(n_seg);
   p.seg_docs = seg_docs;

@@ -209,7 +209,7 @@ def _int32_at(ptr: int, device) -> torch.Tensor:
     import ctypes as C
 
     class _Arr:
-        __cuda_array_interface__ = {"shape": (1,), "typestr": "<i4", "data": (int(ptr), True), "version": 3}
+        __cuda_array_interface__ = {"shape": (1,), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
     return torch.as_tensor(_Arr(), device=device)
 
 
