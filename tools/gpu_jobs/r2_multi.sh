@@ -21,5 +21,5 @@ run c3 --steps 100 --warmup 10
 run c3_nccl --steps 100 --warmup 10 --exchange nccl
 run c3_sync --steps 100 --warmup 10 --sync
 run c4 --workload c4 --steps 30 --warmup 5
-run c4_nccl --workload c4 --steps 30 --warmup 5 --exchange nccl
+if [ "$N" -lt 8 ]; then run c4_nccl --workload c4 --steps 30 --warmup 5 --exchange nccl; fi
 if [ "$N" -ge 8 ]; then run c5 --workload c5; fi

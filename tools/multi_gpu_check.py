@@ -62,6 +62,35 @@ def main():
             if rank == 0:
                 print(f"[multi-gpu G={world} {fn.__name__} exchange={mode}] {res['what']}: {bool(res['ok'])}", flush=True)
             ok &= bool(res["ok"])
+    # the agreement path: rank 0 alone admits nothing (VFI_OPT_TAU_HINT = 2), so every certificate of ITS shard fails; the fail
+    # bit travels with the exchange, rank 0 repairs with the exact streaming scorer and ALL ranks exchange the batch again
+    for mode in ("peer", "nccl"):
+        n, d, nq, k = 90_000, 128, 70, 50
+        xb = synth.dense_corpus_np(n, d, 123)
+        xq = synth.dense_queries_np(nq, d, 123, xb)
+        lo, hi = shard_bounds(n, world, rank)
+        idx = DenseIndex(d, store="bf16", device=dev, id_offset=lo)
+        idx.add(xb[lo:hi])
+        idx.set_option(N.OPT_FORCE_PATH, N.PATH_FUSED)
+        idx.set_option(N.OPT_TAU_HINT, 2 if rank == 0 else 1)
+        D0, I0 = flat_ip.search(xq, xb, k)
+        s = make_sharded_dense(idx, exchange=mode, max_nq=nq, max_k=k)
+        q = torch.from_numpy(xq).to(dev)
+        t1, t2 = s.search_begin(q, k), s.search_begin(q, k)
+        good = True
+        for t in (t1, t2):
+            ids, scores = s.search_finish(t)
+            torch.cuda.synchronize()
+            good &= bool((ids.cpu().numpy() == I0).all() and (scores.cpu().numpy() == D0).all())
+        good &= s.re_exchanges == 2
+        flag = torch.tensor([1 if good else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"[multi-gpu G={world} repair on one rank, exchange={mode}] every rank re-exchanged and equals the oracle: {bool(flag.item())}", flush=True)
+        ok &= bool(flag.item())
+        if s.exchange is not None:
+            s.exchange.close()
+        idx.close()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
