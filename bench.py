@@ -414,26 +414,46 @@ def run_dense(args, name, w, ctx, config, steps, warmup, result_out):
             prev = t
         searcher.search_finish(prev)
 
+    e2e_stream = torch.cuda.Stream(device=ctx.dev).cuda_stream if args.e2e_stream == "caller" else None
+
     def run_e2e_host_call(k_steps):
         for _ in range(k_steps):   # the reference-facing host call of the C ABI: H2D, search, D2H inside
-            index.search_host_into(q_pin[0].data_ptr(), w["b"], w["k"], out_s_pin[0].data_ptr(), out_i_pin[0].data_ptr())
+            index.search_host_into(q_pin[0].data_ptr(), w["b"], w["k"], out_s_pin[0].data_ptr(), out_i_pin[0].data_ptr(), e2e_stream)
+
+    copy_stream = torch.cuda.Stream(device=ctx.dev)
+    h2d_done = [torch.cuda.Event() for _ in range(n_buf)]
+    res_ready = [torch.cuda.Event() for _ in range(n_buf)]
 
     def run_e2e_pipelined(k_steps):
         """Host buffers through the sharded searcher: per batch a pinned H2D copy of its queries, the search (+ exchange),
-        a D2H read of its ids and scores; two batches in flight."""
+        a D2H read of its ids and scores; two batches in flight.  The copies run on a second stream (H2D of batch i+1 and
+        D2H of batch i-1 overlap the kernels of batch i) and every one of them lies inside the timed region."""
+        main = torch.cuda.current_stream(ctx.dev)
+        copy_stream.wait_stream(main)
+
+        def drain(prev):
+            ids, scores = searcher.search_finish(prev[0])
+            res_ready[prev[1]].record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(res_ready[prev[1]])
+                out_i_pin[prev[1]].copy_(ids, non_blocking=True)
+                out_s_pin[prev[1]].copy_(scores, non_blocking=True)
+                ids.record_stream(copy_stream)
+                scores.record_stream(copy_stream)
+
         prev = None
         for i in range(k_steps):
             s = i % n_buf
-            q_stage[s].copy_(q_pin[s], non_blocking=True)
+            with torch.cuda.stream(copy_stream):
+                q_stage[s].copy_(q_pin[s], non_blocking=True)
+                h2d_done[s].record(copy_stream)
+            main.wait_event(h2d_done[s])
             t = searcher.search_begin(q_stage[s], w["k"])
             if prev is not None:
-                ids, scores = searcher.search_finish(prev[0])
-                out_i_pin[prev[1]].copy_(ids, non_blocking=True)
-                out_s_pin[prev[1]].copy_(scores, non_blocking=True)
+                drain(prev)
             prev = (t, s)
-        ids, scores = searcher.search_finish(prev[0])
-        out_i_pin[prev[1]].copy_(ids, non_blocking=True)
-        out_s_pin[prev[1]].copy_(scores, non_blocking=True)
+        drain(prev)
+        main.wait_stream(copy_stream)
         torch.cuda.synchronize()
 
     run_e2e = run_e2e_host_call if ctx.world == 1 else run_e2e_pipelined
@@ -786,6 +806,8 @@ def main():
     ap.add_argument("--hint", type=int, default=1)
     ap.add_argument("--pair", type=int, default=None, help="VFI_OPT_CTA_PAIR (1 = single-CTA kernel, for comparison)")
     ap.add_argument("--tau-m", type=int, default=0, help="VFI_OPT_TAU_M (0 auto, 8/16/32: admission hint = m-th best of a row sample)")
+    ap.add_argument("--e2e-stream", default="own", choices=["own", "caller"],
+                    help="N=1 e2e host call: the library's pooled stream (default) or a stream supplied by the caller")
     ap.add_argument("--sync", action="store_true", help="one synchronous search (+ exchange) per step instead of two batches in flight")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: fused peer-memory push+merge kernel over NVLink, or NCCL all-gather + merge kernel")

@@ -109,6 +109,38 @@ def test_denser_admission_samples_do_not_change_results(torch_cuda, m):
     idx.close()
 
 
+@pytest.mark.parametrize("n,d,nq,k,store,hint", [
+    (150_001, 128, 9, 100, "bf16", 1),     # smallest batch past the streaming scorers, ragged last corpus tile
+    (90_000, 1024, 64, 100, "bf16", 1),    # the largest resident query block (128 KB)
+    (60_000, 256, 33, 10, "bf16", 0),      # no admission hint: thresholds rise by buffer compaction alone
+    (70_000, 100, 20, 50, "f32", 1),       # fp32 rows: 3-term split, K' = 384
+    (50_000, 64, 48, 300, "bf16", 1),      # k' = 384: the deep-list tail behind the swapped kernel
+])
+def test_small_batch_swapped_kernel_matches_oracle(torch_cuda, n, d, nq, k, store, hint):
+    """K1s (corpus rows on the M side of the MMA, the query block resident in shared memory) against the oracle, and against
+    the pair kernel it replaces for 9..64 queries."""
+    torch = torch_cuda
+    from oracle import flat_ip
+    from veritasfi_b200 import _native as N
+    from veritasfi_b200.dense import DenseIndex
+    xb, xq = _world(n, d, nq, 59, store == "bf16")
+    xb[n // 2: n // 2 + 40] = xb[3]                      # duplicates: ties inside one tile
+    xq[0] = xb[3]
+    idx = DenseIndex(d, store=store)
+    idx.add(xb)
+    idx.set_option(N.OPT_FORCE_PATH, N.PATH_FUSED)
+    idx.set_option(N.OPT_TAU_HINT, hint)
+    q = torch.from_numpy(xq).cuda()
+    ids, scores = idx.search_batch(q, k)
+    D0, I0 = flat_ip.search(xq, xb, k)
+    assert (ids.cpu().numpy() == I0).all()
+    assert (scores.cpu().numpy() == D0).all()
+    idx.set_option(N.OPT_SMALL_BATCH, 1)                 # the pair kernel on the same batch
+    ids2, scores2 = idx.search_batch(q, k)
+    assert torch.equal(ids, ids2) and torch.equal(scores, scores2)
+    idx.close()
+
+
 def test_global_ids_must_fit_32_bits(torch_cuda):
     from veritasfi_b200 import _native as N
     from veritasfi_b200.dense import DenseIndex

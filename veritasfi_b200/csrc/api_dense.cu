@@ -13,6 +13,7 @@
 
 #include "api_common.h"
 #include "dense_fused.cuh"
+#include "dense_small.cuh"
 #include "dense_support.cuh"
 #include "exact_stream.cuh"
 
@@ -163,7 +164,7 @@ struct vfi_index {
   DevBuf stage;            // add()/read_rows staging (writer lock / own lock)
   std::mutex stage_mu;
   // options (written under the writer lock)
-  int64_t opt_overfetch = 0, opt_force_path = 0, opt_profile = 0, opt_tau_hint = 1, opt_num_ctas = 0, opt_cta_pair = 0, opt_tau_m = 0;
+  int64_t opt_overfetch = 0, opt_force_path = 0, opt_profile = 0, opt_tau_hint = 1, opt_num_ctas = 0, opt_cta_pair = 0, opt_tau_m = 0, opt_small = 0;
   std::shared_mutex rw;    // searches share it, add/reserve/options own it
   std::mutex pool_mu;      // workspace pool, tickets, stats
   std::vector<std::unique_ptr<Workspace>> pool;
@@ -237,6 +238,7 @@ int vfi_index_create(int d, int store_dtype, int device, vfi_index_t** out) {
     cudaFuncSetAttribute(vfi::dense_fused_pair_kernel<vfi::MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kPairSmemBytes);
     cudaFuncSetAttribute(vfi::dense_fused_pair_kernel<vfi::MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kPairSmemBytes);
     cudaFuncSetAttribute(vfi::dense_fused_pair_kernel<vfi::MODE_CHUNKMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kPairSmemBytes);
+    cudaFuncSetAttribute(vfi::dense_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     GemvAttr<uint16_t, 1>::run(); GemvAttr<uint16_t, 2>::run(); GemvAttr<uint16_t, 3>::run(); GemvAttr<uint16_t, 4>::run();
     GemvAttr<uint16_t, 5>::run(); GemvAttr<uint16_t, 6>::run(); GemvAttr<uint16_t, 7>::run(); GemvAttr<uint16_t, 8>::run();
     GemvAttr<float, 1>::run(); GemvAttr<float, 2>::run(); GemvAttr<float, 3>::run(); GemvAttr<float, 4>::run();
@@ -404,6 +406,10 @@ int vfi_index_set_option(vfi_index_t* idx, int opt, int64_t value) {
     case VFI_OPT_TAU_M:
       if (value != 0 && value != 8 && value != 16 && value != 32) return fail(VFI_ERR_INVALID, "VFI_OPT_TAU_M: 0 auto, 8, 16 or 32");
       idx->opt_tau_m = value;
+      break;
+    case VFI_OPT_SMALL_BATCH:
+      if (value < 0 || value > 1) return fail(VFI_ERR_INVALID, "VFI_OPT_SMALL_BATCH: 0 auto (swapped-operand kernel for 9..64 queries), 1 off");
+      idx->opt_small = value;
       break;
     case VFI_OPT_CTA_PAIR:
       if (value < 0 || value > 2) return fail(VFI_ERR_INVALID, "VFI_OPT_CTA_PAIR: 0 auto, 1 off, 2 on");
@@ -615,6 +621,47 @@ int launch_fused(vfi_index* idx, Workspace* ws, int nq, int keep, int mode, floa
   return VFI_OK;
 }
 
+// K1s: batches of up to 64 queries whose bf16 operand block fits shared memory (dense_small.cuh)
+bool small_ok(const vfi_index* idx, int nq) {
+  const int64_t nq_pad = round_up(nq, 16);
+  return idx->opt_small == 0 && nq_pad <= vfi::kSmMaxQ && nq_pad * idx->kp * 2 <= vfi::kSmQBudget;
+}
+
+int launch_small(vfi_index* idx, Workspace* ws, int nq, int keep, const float* tau, int* o_groups, int* o_nq_pad, int* o_cap,
+                 cudaStream_t st) {
+  const int nq_pad = static_cast<int>(round_up(nq, 16));
+  const int n_tiles = static_cast<int>(ceil_div(idx->n, vfi::kSmTileRows));
+  const int n_ctas = std::max(1, std::min(idx->num_sms, n_tiles));
+  const int cap = 2 * keep + 160;
+  const int nkb = static_cast<int>(idx->kp / 64);
+  CUtensorMap tq, td;
+  VFI_TRY(make_tmap(&tq, ws->qg.p, nq, idx->kp, idx->kp, nq_pad));
+  VFI_TRY(make_tmap(&td, idx->g, idx->n, idx->kp, idx->kp, vfi::kSmTileRows));
+  VFI_TRY(ws->cand.ensure(static_cast<size_t>(n_ctas) * nq_pad * cap * 8));
+  VFI_TRY(ws->cand_count.ensure(static_cast<size_t>(n_ctas) * nq_pad * 4));
+  vfi::SmallParams p{};
+  p.nq = nq;
+  p.nq_pad = nq_pad;
+  p.n_rows = static_cast<int>(idx->n);
+  p.n_kblocks = nkb;
+  p.n_tiles = n_tiles;
+  p.keep = keep;
+  p.cap = cap;
+  p.cand = ws->cand.as<uint64_t>();
+  p.cand_count = ws->cand_count.as<uint32_t>();
+  p.tau_init = tau;
+  const bool prof = idx->opt_profile != 0;
+  if (prof) cudaEventRecord(ws->pev[0], st);
+  vfi::dense_small_kernel<<<n_ctas, vfi::kSmThreads, vfi::dense_small_smem(nq_pad, nkb), st>>>(tq, td, p);
+  LAUNCHED();
+  if (prof) cudaEventRecord(ws->pev[1], st);
+  VFI_CUDA(cudaGetLastError());
+  *o_groups = n_ctas;
+  *o_nq_pad = nq_pad;
+  *o_cap = cap;
+  return VFI_OK;
+}
+
 struct LaunchInfo {
   int path = 0, keep = 0;
   bool fused = false;
@@ -713,7 +760,9 @@ int search_launch(vfi_index* idx, Workspace* ws, const float* q_dev, int nq, int
       tau = ws->tau.as<float>();
     }
   }
-  if (path == 2) {
+  if (path == 2 && small_ok(idx, nq)) {
+    VFI_TRY(launch_small(idx, ws, nq, keep, tau, &n_groups, &nq_pad, &cap, st));
+  } else if (path == 2) {
     VFI_TRY(launch_fused(idx, ws, nq, keep, vfi::MODE_TOPK, nullptr, 0, tau, &n_groups, &nq_pad, &cap, st));
   } else {
     // streaming scorer: per-CTA shared key buffers

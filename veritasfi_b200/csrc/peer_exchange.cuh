@@ -120,13 +120,25 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const ExchangeParam
       if (v & 1u) s_fail = 1;
     }
     __syncthreads();
-    WindowSrc src{my_win, p.world, p.k, q, p.max_nq, p.max_k};
-    const uint32_t n = block_topk(src, static_cast<uint32_t>(p.world * p.k), static_cast<uint32_t>(p.k_out), sm);
-    for (int i = threadIdx.x; i < p.k_out; i += blockDim.x) {
-      const bool has = static_cast<uint32_t>(i) < n;
-      const uint64_t key = has ? sm->keys[i] : 0ull;
-      p.out_scores[static_cast<int64_t>(q) * p.k_out + i] = has ? key_score(key) : -3.402823466e+38f;
-      p.out_ids[static_cast<int64_t>(q) * p.k_out + i] = has ? static_cast<int64_t>(key_id(key)) : -1;
+    const int n_all = p.world * p.k;
+    bool merged = false;
+    if (n_all <= static_cast<int>(kSortCap)) {
+      for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
+        const int r = i / p.k, j = i - r * p.k;
+        sm->keys[i] = __ldcg(my_win + (static_cast<int64_t>(r) * p.max_nq + q) * p.max_k + j);   // L2: peers wrote it
+      }
+      __syncthreads();
+      merged = merge_sorted_rows(sm->keys, p.world, p.k, p.k_out, q, p.out_scores, p.out_ids);
+    }
+    if (!merged) {
+      WindowSrc src{my_win, p.world, p.k, q, p.max_nq, p.max_k};
+      const uint32_t n = block_topk(src, static_cast<uint32_t>(p.world * p.k), static_cast<uint32_t>(p.k_out), sm);
+      for (int i = threadIdx.x; i < p.k_out; i += blockDim.x) {
+        const bool has = static_cast<uint32_t>(i) < n;
+        const uint64_t key = has ? sm->keys[i] : 0ull;
+        p.out_scores[static_cast<int64_t>(q) * p.k_out + i] = has ? key_score(key) : -3.402823466e+38f;
+        p.out_ids[static_cast<int64_t>(q) * p.k_out + i] = has ? static_cast<int64_t>(key_id(key)) : -1;
+      }
     }
     __syncthreads();   // sm is reused by the next query
   }

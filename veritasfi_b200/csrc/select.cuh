@@ -91,6 +91,59 @@ __device__ __forceinline__ uint32_t block_topk_smem(SM* sm, uint32_t n, uint32_t
   return min(n, k);
 }
 
+// Merge of `rows` result rows of k keys each, staged in shared memory (row r at keys + r*k), into the k_out best of result
+// row q.  Every producer in this library emits its rows in result order (score desc, id asc = key descending, padding 0
+// last), so the global rank of a key is its place in its own row plus, for every other row, the number of keys above it
+// there (binary search; keys of different rows never compare equal: ids are unique) — no sort, ~log2(k) steps x rows per
+// key.  Returns false without writing anything when some row is NOT in order (the caller then selects generically).
+// All threads of the block must call; ids are written as they are in the keys (global ids).
+__device__ inline bool merge_sorted_rows(const uint64_t* keys, int rows, int k, int k_out, int64_t q,
+                                         float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+  __shared__ uint32_t s_unsorted, s_valid;
+  const int n_all = rows * k;
+  if (threadIdx.x == 0) { s_unsorted = 0; s_valid = 0; }
+  __syncthreads();
+  bool bad = false;
+  uint32_t valid_mine = 0;
+  for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
+    const uint64_t key = keys[i];
+    valid_mine += key != kKeyNone;
+    if (i % k > 0 && (key > keys[i - 1] || (key == keys[i - 1] && key != kKeyNone))) bad = true;
+  }
+  if (bad) s_unsorted = 1;
+  if (valid_mine) atomicAdd(&s_valid, valid_mine);
+  __syncthreads();
+  const bool ok = s_unsorted == 0;
+  if (ok) {
+    for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
+      const uint64_t key = keys[i];
+      if (key == kKeyNone) continue;
+      const int r = i / k;
+      int rank = i - r * k;
+      for (int r2 = 0; r2 < rows; ++r2) {
+        if (r2 == r) continue;
+        const uint64_t* row = keys + r2 * k;
+        int lo = 0, hi = k;                           // first position whose key is below `key`
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (row[mid] > key) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+      }
+      if (rank < k_out) {
+        out_scores[q * k_out + rank] = key_score(key);
+        out_ids[q * k_out + rank] = static_cast<int64_t>(key_id(key));
+      }
+    }
+    for (int i = threadIdx.x + static_cast<int>(s_valid); i < k_out; i += blockDim.x) {     // fewer than k_out real keys
+      out_scores[q * k_out + i] = -3.402823466e+38f;
+      out_ids[q * k_out + i] = -1;
+    }
+  }
+  __syncthreads();
+  return ok;
+}
+
 // Src: struct with   template<class F> __device__ void for_each(F f) const
 // calling f(key) for the keys assigned to this thread (each key visited by exactly one thread).
 // Leaves the min(total,k) best keys sorted descending in sm->keys[0..); returns that count.

@@ -412,6 +412,16 @@ __global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ sc
   extern __shared__ uint8_t smem_raw[];
   SelectSmem* sm = reinterpret_cast<SelectSmem*>(smem_raw);
   const int q = blockIdx.x;
+  if (g * k_in <= static_cast<int>(kSortCap)) {     // rows in result order (every searcher here emits them so): rank by search
+    for (int i = threadIdx.x; i < g * k_in; i += blockDim.x) {
+      const int gi = i / k_in, r = i % k_in;
+      const int64_t o = (static_cast<int64_t>(gi) * nq + q) * k_in + r;
+      const int64_t id = ids[o];
+      sm->keys[i] = (id >= 0) ? make_key(scores[o], static_cast<uint32_t>(id)) : kKeyNone;
+    }
+    __syncthreads();
+    if (merge_sorted_rows(sm->keys, g, k_in, k_out, q, out_scores, out_ids)) return;
+  }
   MergeSrc src{scores, ids, g, nq, k_in, q};
   const uint32_t n = block_topk(src, static_cast<uint32_t>(g) * k_in, static_cast<uint32_t>(k_out), sm);
   for (int i = threadIdx.x; i < k_out; i += blockDim.x) {

@@ -144,10 +144,11 @@ class DenseIndex:
                                               N.MEM_HOST, None))
         return ids, scores
 
-    def search_host_into(self, q_ptr: int, B: int, k: int, scores_ptr: int, ids_ptr: int) -> None:
-        """Same as search_host on caller-owned (e.g. pinned) buffers given by address."""
+    def search_host_into(self, q_ptr: int, B: int, k: int, scores_ptr: int, ids_ptr: int, stream: int | None = None) -> None:
+        """Same as search_host on caller-owned (e.g. pinned) buffers given by address.  stream: a cudaStream_t value; None =
+        the call's own stream from the workspace pool (concurrent callers overlap)."""
         N.check(N.load().vfi_index_search(self._h, C.c_void_p(q_ptr), B, int(k), C.c_void_p(scores_ptr),
-                                          C.c_void_p(ids_ptr), N.MEM_HOST, None))
+                                          C.c_void_p(ids_ptr), N.MEM_HOST, C.c_void_p(stream) if stream else None))
 
     # -- SURVEY.md §8f N2: persist / reload a shard -------------------------------------------------
     def read_rows(self, first: int = 0, n: int | None = None) -> np.ndarray:

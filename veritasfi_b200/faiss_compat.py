@@ -35,8 +35,10 @@ def _as_f32_matrix(x, what: str) -> np.ndarray:
     return x
 
 
-def normalize_L2(x: np.ndarray, device: int = 0) -> None:
+def normalize_L2(x: np.ndarray, device: int | None = None) -> None:
     """In-place row-wise L2 normalisation (zero rows untouched) — faiss.normalize_L2."""
+    import os
+    device = int(os.environ.get("VFI_DEVICE", "0")) if device is None else int(device)
     x = _as_f32_matrix(x, "normalize_L2")
     if not x.flags.writeable:
         raise ValueError("normalize_L2: array is read-only")
@@ -52,11 +54,17 @@ class IndexFlatIP:
     metric_type = METRIC_INNER_PRODUCT
     is_trained = True
 
-    def __init__(self, d: int, device: int = 0, store: str = "f32"):
+    def __init__(self, d: int, device: int | None = None, store: str | None = None):
+        # the reference constructs `faiss.IndexFlatIP(dimension)` (faissRetriever.py:18): where the index lives and how rows
+        # are stored come from the environment when the caller does not say (VFI_DEVICE, default 0; VFI_STORE, default f32 =
+        # faiss semantics on the fp32 values, bf16 = the rows are defined as their bf16 roundings)
+        import os
         self._h = C.c_void_p()
         self.d = int(d)
-        self.device = int(device)
+        self.device = int(os.environ.get("VFI_DEVICE", "0")) if device is None else int(device)
+        store = os.environ.get("VFI_STORE", "f32") if store is None else store
         store_code = {"f32": N.STORE_F32, "bf16": N.STORE_BF16}[store]
+        self._store_code = store_code
         N.check(N.load().vfi_index_create(self.d, store_code, self.device, C.byref(self._h)))
 
     # -- faiss surface ---------------------------------------------------------------------
@@ -93,7 +101,7 @@ class IndexFlatIP:
 
     def reset(self) -> None:
         self.close()
-        N.check(N.load().vfi_index_create(self.d, N.STORE_F32, self.device, C.byref(self._h)))
+        N.check(N.load().vfi_index_create(self.d, self._store_code, self.device, C.byref(self._h)))
 
     # -- extensions ------------------------------------------------------------------------
     def set_option(self, opt: int, value: int) -> None:
