@@ -387,6 +387,8 @@ def run_dense(args, name, w, ctx, config, steps, warmup, result_out):
     if args.pair is not None:
         index.set_option(N.OPT_CTA_PAIR, args.pair)
     index.set_option(N.OPT_TAU_M, args.tau_m)
+    if args.no_small:
+        index.set_option(N.OPT_SMALL_BATCH, 1)
     searcher = make_sharded_dense(index, exchange=args.exchange, max_nq=w["b"], max_k=w["k"])
     q_dev = synth.dense_queries_torch(w["b"], w["d"], SEED, ctx.dev)
     n_buf = 3
@@ -498,7 +500,8 @@ def run_dense(args, name, w, ctx, config, steps, warmup, result_out):
                         "traffic_source": "ncu dram__bytes_read+write per launch, profiles/ncu_traffic.json",
                         "hbm_frac": gbs / peaks["hbm"]}
         else:
-            kname = {N.PATH_FUSED: "dense_fused_pair_kernel<MODE_TOPK>", N.PATH_GEMV: "gemv_topk_kernel", N.PATH_EXACT: "exact_scores_kernel"}[path]
+            kname = {N.PATH_FUSED: "dense_small_kernel (swapped operands, query block resident)" if 8 < w["b"] <= 64 and not args.no_small
+                     else "dense_fused_pair_kernel<MODE_TOPK>", N.PATH_GEMV: "gemv_topk_kernel", N.PATH_EXACT: "exact_scores_kernel"}[path]
             roofline = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                         "traffic": read_traffic(name) if ctx.world == 1 else None, "kernel": kname, "kernel_ms": kernel_ms,
                         "peak_source": f"{peaks['source']} MEASURED_PEAKS.json hbm_gbs",
@@ -806,6 +809,7 @@ def main():
     ap.add_argument("--hint", type=int, default=1)
     ap.add_argument("--pair", type=int, default=None, help="VFI_OPT_CTA_PAIR (1 = single-CTA kernel, for comparison)")
     ap.add_argument("--tau-m", type=int, default=0, help="VFI_OPT_TAU_M (0 auto, 8/16/32: admission hint = m-th best of a row sample)")
+    ap.add_argument("--no-small", action="store_true", help="batches of 9..64 queries on the pair kernel instead of the swapped-operand kernel")
     ap.add_argument("--e2e-stream", default="own", choices=["own", "caller"],
                     help="N=1 e2e host call: the library's pooled stream (default) or a stream supplied by the caller")
     ap.add_argument("--sync", action="store_true", help="one synchronous search (+ exchange) per step instead of two batches in flight")

@@ -19,4 +19,3 @@ done
 for m in 0 16; do
   python bench.py --workload c3s8 --no-cpu-baseline --tau-m $m 2>gpurun_out/e.err > gpurun_out/x_c3s8_m$m.json || tail -5 gpurun_out/e.err; show x_c3s8_m$m
 done
-python tools/bench_extra.py bm25 2>gpurun_out/e.err | tail -1 | cut -c1-600

@@ -51,6 +51,7 @@ def main():
         return
     index, lo, hi = bench.build_dense_index(ctx, w["n"], w["d"], bench.SEED)
     index.set_option(N.OPT_TAU_M, args.tau_m)
+    index.set_option(N.OPT_PROFILE, 0)
     q = synth.dense_queries_torch(w["b"], w["d"], bench.SEED, ctx.dev)
     for _ in range(args.warmup + args.steps):
         index.search_batch(q, w["k"])

@@ -7,6 +7,9 @@
 // Workspace of its own taken from a pool (device scratch, prepared queries, certificate flag, events, a private stream
 // for host-buffer calls), so any number of threads may search one index at once; add/reserve/set_option take the writer
 // lock (not concurrent with search, as with faiss).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <shared_mutex>
 #include <unordered_map>
@@ -918,6 +921,10 @@ int vfi_index_search(vfi_index_t* idx, const float* q, int64_t nq, int k, float*
     idx->stats.searches++;
     idx->stats.queries += nq;
   }
+  // VFI_TRACE_HOST=1: wall-clock phases of the host-buffer call on stderr (debugging aid for the e2e number)
+  static const bool trace = std::getenv("VFI_TRACE_HOST") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_in = trace ? now() : 0.0, t_launch = 0.0, t_finish = 0.0;
   int rc = VFI_OK;
   for (int64_t q0 = 0; q0 < nq && rc == VFI_OK; q0 += kMaxQueriesPerLaunch) {
     const int nb = static_cast<int>(std::min<int64_t>(kMaxQueriesPerLaunch, nq - q0));
@@ -937,7 +944,9 @@ int vfi_index_search(vfi_index_t* idx, const float* q, int64_t nq, int k, float*
       LaunchInfo info;
       VFI_TRY(search_launch(idx, ws, qd, nb, k, os, oi, st, false, &info));
       note_launch(idx, info);
+      if (trace) t_launch = now();
       VFI_TRY(search_finish(idx, ws));
+      if (trace) t_finish = now();
       if (mem == VFI_MEM_HOST) {
         VFI_CUDA(cudaMemcpyAsync(out_scores + q0 * k, os, static_cast<size_t>(nb) * k * 4, cudaMemcpyDeviceToHost, st));
         VFI_CUDA(cudaMemcpyAsync(out_ids + q0 * k, oi, static_cast<size_t>(nb) * k * 8, cudaMemcpyDeviceToHost, st));
@@ -948,6 +957,9 @@ int vfi_index_search(vfi_index_t* idx, const float* q, int64_t nq, int k, float*
     rc = body();
   }
   if (rc != VFI_OK) cudaStreamSynchronize(st);   // nothing of this call may still be using the workspace
+  if (trace)
+    std::fprintf(stderr, "[vfi trace] search nq=%lld: enqueue %.3f ms, wait for the batch %.3f ms, results out %.3f ms\n",
+                 static_cast<long long>(nq), t_launch - t_in, t_finish - t_launch, now() - t_finish);
   release_ws(idx, ws);
   return rc;
 }
