@@ -62,6 +62,10 @@ enum { VFI_MEM_HOST = 0, VFI_MEM_DEVICE = 1 };
  *                   tensor-core pass runs on a 3-term bf16 split, the exact pass on the fp32 rows. */
 enum { VFI_STORE_BF16 = 0, VFI_STORE_F32 = 1 };
 
+/* element type of a query buffer (vfi_index_search_ex): fp32, or raw bf16 bit patterns (half the H2D bytes; exactly what a
+ * VFI_STORE_BF16 index would round the queries to anyway) */
+enum { VFI_DTYPE_F32 = 0, VFI_DTYPE_BF16 = 1 };
+
 #define VFI_MAX_K 2048
 
 typedef struct vfi_index vfi_index_t;
@@ -100,6 +104,9 @@ int vfi_index_pairwise(vfi_index_t* idx, const int64_t* ids, int n, float* out, 
  * VFI_MEM_DEVICE the call returns after the device work is enqueued and verified. */
 int vfi_index_search(vfi_index_t* idx, const float* q, int64_t nq, int k, float* out_scores,
                      int64_t* out_ids, int mem, void* stream);
+/* the same with the query element type given (q: [nq,d] of q_dtype) */
+int vfi_index_search_ex(vfi_index_t* idx, const void* q, int q_dtype, int64_t nq, int k, float* out_scores,
+                        int64_t* out_ids, int mem, void* stream);
 
 /* Threading: vfi_index_search, vfi_index_search_begin/finish, vfi_index_pairwise, vfi_index_read_rows and
  * vfi_index_reconstruct may be called from any number of threads on one index at the same time (the reference calls
@@ -114,6 +121,8 @@ int vfi_index_search(vfi_index_t* idx, const float* q, int64_t nq, int k, float*
  * before finishing batch i never leaves the GPU idle during the host's look at the certificate flag. */
 int vfi_index_search_begin(vfi_index_t* idx, const float* q, int64_t nq, int k, float* out_scores,
                            int64_t* out_ids, void* stream, int* ticket);
+int vfi_index_search_begin_ex(vfi_index_t* idx, const void* q, int q_dtype, int64_t nq, int k, float* out_scores,
+                              int64_t* out_ids, void* stream, int* ticket);
 int vfi_index_search_finish(vfi_index_t* idx, int ticket);
 /* device address of the batch's certificate counter (> 0 once its kernels ran = some query still needs the repair of
  * finish()); valid until finish(ticket).  Lets a kernel enqueued behind the batch (vfi_exchange_merge_flagged) tell its

@@ -141,6 +141,55 @@ def test_small_batch_swapped_kernel_matches_oracle(torch_cuda, n, d, nq, k, stor
     idx.close()
 
 
+@pytest.mark.parametrize("store", ["bf16", "f32"])
+def test_bf16_query_buffers_give_the_bits_of_fp32_buffers(torch_cuda, store):
+    """vfi_index_search_ex with VFI_DTYPE_BF16 queries (half the H2D bytes) == the same values passed as fp32, on all paths."""
+    torch = torch_cuda
+    from oracle import flat_ip
+    from veritasfi_b200.dense import DenseIndex
+    xb, xq = _world(40_000, 192, 70, 61, True)           # queries already bf16-representable
+    idx = DenseIndex(192, store=store)
+    idx.add(xb)
+    D0, I0 = flat_ip.search(xq, xb, 20)
+    for nq in (70, 20, 3):                               # pair kernel, small-batch kernel, streaming GEMV
+        q32 = torch.from_numpy(xq[:nq]).cuda()
+        ids, scores = idx.search_batch(q32.to(torch.bfloat16), 20)
+        assert (ids.cpu().numpy() == I0[:nq]).all() and (scores.cpu().numpy() == D0[:nq]).all()
+        t = idx.search_begin(q32.to(torch.bfloat16), 20)
+        i2, s2 = idx.search_finish(t)
+        assert torch.equal(i2, ids) and torch.equal(s2, scores)
+    idx.close()
+
+
+def test_random_shapes_on_every_dense_path(torch_cuda):
+    """A seeded sweep of ragged shapes (d not a multiple of 64, n not a multiple of the tile, k from 1 to 300, both stores)
+    through whatever path the library picks: exact streaming, GEMV, small-batch kernel, pair kernel."""
+    torch = torch_cuda
+    from oracle import flat_ip
+    from veritasfi_b200.dense import DenseIndex
+    rng = np.random.default_rng(2026)
+    seen = set()
+    fixed = {14: (30_000, 768, 3, 10, "f32"), 15: (4_100, 48, 70, 5, "bf16"), 16: (9_000, 64, 4, 2000, "bf16")}   # exact streaming scorer
+    for case in range(17):
+        n = int(rng.integers(4_200, 60_000))
+        d = int(rng.choice([33, 48, 64, 100, 200, 384, 768]))
+        nq = int(rng.choice([1, 2, 5, 8, 9, 17, 40, 64, 65, 129, 200]))
+        k = int(rng.choice([1, 3, 10, 64, 100, 257]))
+        store = "bf16" if case % 2 == 0 else "f32"
+        if case in fixed:
+            n, d, nq, k, store = fixed[case]
+        xb, xq = _world(n, d, nq, 700 + case, store == "bf16")
+        idx = DenseIndex(d, store=store)
+        idx.add(xb)
+        ids, scores = idx.search_batch(torch.from_numpy(xq).cuda(), k)
+        D0, I0 = flat_ip.search(xq, xb, k)
+        assert (ids.cpu().numpy() == I0).all(), (case, n, d, nq, k, store)
+        assert (scores.cpu().numpy() == D0).all(), (case, n, d, nq, k, store)
+        seen.add(idx.stats().last_path)
+        idx.close()
+    assert seen == {1, 2, 3}
+
+
 def test_global_ids_must_fit_32_bits(torch_cuda):
     from veritasfi_b200 import _native as N
     from veritasfi_b200.dense import DenseIndex

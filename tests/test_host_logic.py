@@ -116,6 +116,17 @@ def _gloo_worker(rank, world, port, n, d, k, out_path):
     ids, scores = searcher.search(torch.from_numpy(xq), k)
     D0, I0 = fi.search_exhaustive(xq, xb, k)
     ok = bool((ids.numpy() == I0).all() and (scores.numpy() == D0).all())
+    # the hybrid retriever's shape: three per-rank lists travel as 3*B independent rows in ONE exchange (exchange_rows)
+    B, L = 4, 6
+    rows_s, rows_i = [], []
+    for p in range(3):
+        D, I = fi.search_exhaustive(np.roll(xq[:B], p, axis=1), xb[lo:hi], L, id_base=lo)
+        rows_s.append(D)
+        rows_i.append(I)
+    mi, ms = searcher.exchange_rows(torch.from_numpy(np.concatenate(rows_s)), torch.from_numpy(np.concatenate(rows_i)), L)
+    for p in range(3):
+        D, I = fi.search_exhaustive(np.roll(xq[:B], p, axis=1), xb, L)
+        ok &= bool((mi.numpy()[p * B:(p + 1) * B] == I).all() and (ms.numpy()[p * B:(p + 1) * B] == D).all())
     with open(f"{out_path}.{rank}", "w") as f:
         f.write("ok" if ok else "mismatch")
     dist.barrier()

@@ -11,6 +11,7 @@ from .build import LIB_PATH
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_INTERNAL = range(7)
 MEM_HOST, MEM_DEVICE = 0, 1
 STORE_BF16, STORE_F32 = 0, 1
+DTYPE_F32, DTYPE_BF16 = 0, 1
 OPT_OVERFETCH, OPT_FORCE_PATH, OPT_PROFILE, OPT_TAU_HINT, OPT_NUM_CTAS, OPT_CTA_PAIR, OPT_TAU_M, OPT_SMALL_BATCH = 1, 2, 3, 4, 5, 7, 9, 10
 PATH_AUTO, PATH_EXACT, PATH_FUSED, PATH_GEMV = 0, 1, 2, 3
 PATH_EXHAUSTIVE = PATH_EXACT   # the old name: every row scored canonically
@@ -60,6 +61,8 @@ _SIGNATURES = {
     "vfi_index_read_rows": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, _P]),
     "vfi_index_pairwise": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
     "vfi_index_search": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P, C.c_int, _P]),
+    "vfi_index_search_ex": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, _P, _P, C.c_int, _P]),
+    "vfi_index_search_begin_ex": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, _P, _P, _P, C.POINTER(C.c_int)]),
     "vfi_index_set_option": (C.c_int, [_P, C.c_int, C.c_int64]),
     "vfi_index_get_stats": (C.c_int, [_P, C.POINTER(SearchStats), C.c_int]),
     "vfi_index_debug_scores": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, _P]),

@@ -124,7 +124,8 @@ struct Workspace {
   cudaStream_t own = nullptr;    // host-buffer calls that pass no stream run here, so concurrent callers overlap
   // batch state
   bool needs_check = false, used_tau = false, profiled = false;
-  const float* q = nullptr;
+  const void* q = nullptr;
+  int q_dtype = VFI_DTYPE_F32;
   int nq = 0, k = 0;
   float* o_scores = nullptr;
   int64_t* o_ids = nullptr;
@@ -473,18 +474,25 @@ bool gemv_ok(const vfi_index* idx) {
   return bytes <= vfi::kGemvMaxVec * 32 * 16;
 }
 
-int prep_queries(vfi_index* idx, Workspace* ws, const float* q_dev, int nq, cudaStream_t st) {
+int prep_queries(vfi_index* idx, Workspace* ws, const void* q_dev, int q_dtype, int nq, cudaStream_t st) {
   VFI_TRY(ws->qcanon.ensure(static_cast<size_t>(nq) * idx->dp * 4));
   VFI_TRY(ws->qg.ensure(static_cast<size_t>(nq) * idx->kp * 2));
   VFI_TRY(ws->eps.ensure(static_cast<size_t>(nq) * 4));
   const int threads = 256;
   const int blocks = static_cast<int>(ceil_div(static_cast<int64_t>(nq) * 32, threads));
-  if (idx->store == VFI_STORE_F32)
-    vfi::prep_queries_kernel<true><<<blocks, threads, 0, st>>>(q_dev, nq, idx->d, idx->dp, ws->qcanon.as<float>(),
-                                                                ws->qg.as<uint16_t>(), idx->kp, idx->xnorm_bits, ws->eps.as<float>());
-  else
-    vfi::prep_queries_kernel<false><<<blocks, threads, 0, st>>>(q_dev, nq, idx->d, idx->dp, ws->qcanon.as<float>(),
-                                                                 ws->qg.as<uint16_t>(), idx->kp, idx->xnorm_bits, ws->eps.as<float>());
+  float* canon = ws->qcanon.as<float>();
+  uint16_t* qg = ws->qg.as<uint16_t>();
+  float* eps = ws->eps.as<float>();
+  const bool split = idx->store == VFI_STORE_F32;
+  if (q_dtype == VFI_DTYPE_BF16) {
+    const uint16_t* q = static_cast<const uint16_t*>(q_dev);
+    if (split) vfi::prep_queries_kernel<true, uint16_t><<<blocks, threads, 0, st>>>(q, nq, idx->d, idx->dp, canon, qg, idx->kp, idx->xnorm_bits, eps);
+    else vfi::prep_queries_kernel<false, uint16_t><<<blocks, threads, 0, st>>>(q, nq, idx->d, idx->dp, canon, qg, idx->kp, idx->xnorm_bits, eps);
+  } else {
+    const float* q = static_cast<const float*>(q_dev);
+    if (split) vfi::prep_queries_kernel<true, float><<<blocks, threads, 0, st>>>(q, nq, idx->d, idx->dp, canon, qg, idx->kp, idx->xnorm_bits, eps);
+    else vfi::prep_queries_kernel<false, float><<<blocks, threads, 0, st>>>(q, nq, idx->d, idx->dp, canon, qg, idx->kp, idx->xnorm_bits, eps);
+  }
   LAUNCHED();
   VFI_CUDA(cudaGetLastError());
   return VFI_OK;
@@ -672,18 +680,19 @@ struct LaunchInfo {
 
 // Enqueue one batch of <= kMaxQueriesPerLaunch queries already on the device (results to device buffers) in workspace
 // `ws` without waiting: everything up to the copy of the certificate flag.  search_finish() waits and repairs.
-int search_launch(vfi_index* idx, Workspace* ws, const float* q_dev, int nq, int k, float* out_scores, int64_t* out_ids,
+int search_launch(vfi_index* idx, Workspace* ws, const void* q_dev, int q_dtype, int nq, int k, float* out_scores, int64_t* out_ids,
                   cudaStream_t st, bool no_hint, LaunchInfo* info) {
   ws->needs_check = false;
   ws->used_tau = false;
   ws->profiled = false;
   ws->q = q_dev;
+  ws->q_dtype = q_dtype;
   ws->nq = nq;
   ws->k = k;
   ws->o_scores = out_scores;
   ws->o_ids = out_ids;
   ws->st = st;
-  VFI_TRY(prep_queries(idx, ws, q_dev, nq, st));
+  VFI_TRY(prep_queries(idx, ws, q_dev, q_dtype, nq, st));
   VFI_TRY(ws->flag.ensure(static_cast<size_t>(kMaxQueriesPerLaunch + 1) * 4));
   int* d_flag = ws->flag.as<int>();   // [0] number of queries whose certificate failed, [1..] those queries
   VFI_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
@@ -885,7 +894,7 @@ int search_finish(vfi_index* idx, Workspace* ws) {
       idx->stats.hint_retries++;
     }
     LaunchInfo info;
-    VFI_TRY(search_launch(idx, ws, ws->q, ws->nq, ws->k, ws->o_scores, ws->o_ids, ws->st, true, &info));
+    VFI_TRY(search_launch(idx, ws, ws->q, ws->q_dtype, ws->nq, ws->k, ws->o_scores, ws->o_ids, ws->st, true, &info));
     return search_finish(idx, ws);
   }
   {
@@ -904,7 +913,15 @@ extern "C" {
 
 int vfi_index_search(vfi_index_t* idx, const float* q, int64_t nq, int k, float* out_scores, int64_t* out_ids, int mem,
                      void* stream) {
-  if (!idx || (nq > 0 && (!q || !out_scores || !out_ids)) || nq < 0) return fail(VFI_ERR_INVALID, "bad argument to vfi_index_search");
+  return vfi_index_search_ex(idx, q, VFI_DTYPE_F32, nq, k, out_scores, out_ids, mem, stream);
+}
+
+int vfi_index_search_ex(vfi_index_t* idx, const void* q_any, int q_dtype, int64_t nq, int k, float* out_scores, int64_t* out_ids,
+                        int mem, void* stream) {
+  if (!idx || (nq > 0 && (!q_any || !out_scores || !out_ids)) || nq < 0) return fail(VFI_ERR_INVALID, "bad argument to vfi_index_search");
+  if (q_dtype != VFI_DTYPE_F32 && q_dtype != VFI_DTYPE_BF16) return fail(VFI_ERR_INVALID, "q_dtype must be VFI_DTYPE_F32 or VFI_DTYPE_BF16");
+  const size_t qsz = q_dtype == VFI_DTYPE_BF16 ? 2 : 4;
+  const uint8_t* q = static_cast<const uint8_t*>(q_any);
   if (k <= 0) return fail(VFI_ERR_INVALID, "k must be positive");
   if (k > VFI_MAX_K) return fail(VFI_ERR_UNSUPPORTED, "k exceeds VFI_MAX_K (2048)");
   if (nq == 0) return VFI_OK;
@@ -928,21 +945,21 @@ int vfi_index_search(vfi_index_t* idx, const float* q, int64_t nq, int k, float*
   int rc = VFI_OK;
   for (int64_t q0 = 0; q0 < nq && rc == VFI_OK; q0 += kMaxQueriesPerLaunch) {
     const int nb = static_cast<int>(std::min<int64_t>(kMaxQueriesPerLaunch, nq - q0));
-    const float* qd = q + q0 * idx->d;
+    const void* qd = q + static_cast<size_t>(q0) * idx->d * qsz;
     float* os = out_scores + q0 * k;
     int64_t* oi = out_ids + q0 * k;
     auto body = [&]() -> int {
       if (mem == VFI_MEM_HOST) {
-        VFI_TRY(ws->qin.ensure(static_cast<size_t>(nb) * idx->d * 4));
+        VFI_TRY(ws->qin.ensure(static_cast<size_t>(nb) * idx->d * qsz));
         VFI_TRY(ws->out_scores.ensure(static_cast<size_t>(nb) * k * 4));
         VFI_TRY(ws->out_ids.ensure(static_cast<size_t>(nb) * k * 8));
-        VFI_CUDA(cudaMemcpyAsync(ws->qin.p, qd, static_cast<size_t>(nb) * idx->d * 4, cudaMemcpyHostToDevice, st));
-        qd = ws->qin.as<float>();
+        VFI_CUDA(cudaMemcpyAsync(ws->qin.p, qd, static_cast<size_t>(nb) * idx->d * qsz, cudaMemcpyHostToDevice, st));
+        qd = ws->qin.p;
         os = ws->out_scores.as<float>();
         oi = ws->out_ids.as<int64_t>();
       }
       LaunchInfo info;
-      VFI_TRY(search_launch(idx, ws, qd, nb, k, os, oi, st, false, &info));
+      VFI_TRY(search_launch(idx, ws, qd, q_dtype, nb, k, os, oi, st, false, &info));
       note_launch(idx, info);
       if (trace) t_launch = now();
       VFI_TRY(search_finish(idx, ws));
@@ -966,7 +983,13 @@ int vfi_index_search(vfi_index_t* idx, const float* q, int64_t nq, int k, float*
 
 int vfi_index_search_begin(vfi_index_t* idx, const float* q, int64_t nq, int k, float* out_scores, int64_t* out_ids, void* stream,
                            int* ticket) {
+  return vfi_index_search_begin_ex(idx, q, VFI_DTYPE_F32, nq, k, out_scores, out_ids, stream, ticket);
+}
+
+int vfi_index_search_begin_ex(vfi_index_t* idx, const void* q, int q_dtype, int64_t nq, int k, float* out_scores, int64_t* out_ids,
+                              void* stream, int* ticket) {
   if (!idx || !ticket || !q || !out_scores || !out_ids || nq <= 0) return fail(VFI_ERR_INVALID, "bad argument to vfi_index_search_begin");
+  if (q_dtype != VFI_DTYPE_F32 && q_dtype != VFI_DTYPE_BF16) return fail(VFI_ERR_INVALID, "q_dtype must be VFI_DTYPE_F32 or VFI_DTYPE_BF16");
   if (k <= 0) return fail(VFI_ERR_INVALID, "k must be positive");
   if (k > VFI_MAX_K) return fail(VFI_ERR_UNSUPPORTED, "k exceeds VFI_MAX_K (2048)");
   if (nq > kMaxQueriesPerLaunch) return fail(VFI_ERR_UNSUPPORTED, "vfi_index_search_begin takes at most 1024 queries per batch");
@@ -976,7 +999,7 @@ int vfi_index_search_begin(vfi_index_t* idx, const float* q, int64_t nq, int k, 
   Workspace* ws = acquire_ws(idx);
   if (!ws) return VFI_ERR_NOMEM;
   LaunchInfo info;
-  const int rc = search_launch(idx, ws, q, static_cast<int>(nq), k, out_scores, out_ids, static_cast<cudaStream_t>(stream), false, &info);
+  const int rc = search_launch(idx, ws, q, q_dtype, static_cast<int>(nq), k, out_scores, out_ids, static_cast<cudaStream_t>(stream), false, &info);
   if (rc != VFI_OK) {
     cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
     release_ws(idx, ws);
@@ -1134,7 +1157,7 @@ int vfi_index_debug_scores(vfi_index_t* idx, const float* q, int64_t nq, float* 
       VFI_CUDA(cudaMemcpyAsync(ws->qin.p, q, static_cast<size_t>(nq) * idx->d * 4, cudaMemcpyHostToDevice, st));
       qd = ws->qin.as<float>();
     }
-    VFI_TRY(prep_queries(idx, ws, qd, static_cast<int>(nq), st));
+    VFI_TRY(prep_queries(idx, ws, qd, VFI_DTYPE_F32, static_cast<int>(nq), st));
     const int64_t ld = ceil_div(idx->n, vfi::kBN) * vfi::kBN;
     const int64_t nq_pad = round_up(ceil_div(nq, vfi::kBM), 2) * vfi::kBM;
     VFI_TRY(ws->dbg.ensure(static_cast<size_t>(nq_pad) * ld * 4));
@@ -1206,11 +1229,26 @@ int vfi_cosine_topk(const float* e, int64_t n_e, const float* c, int64_t n_c, in
     std::memcpy(&cn[static_cast<size_t>(n_c - 1 - i) * d], c + static_cast<size_t>(i) * d, sizeof(float) * d);
   VFI_TRY(vfi_normalize_l2(cn.data(), n_c, d, VFI_MEM_HOST, device, stream));
   VFI_TRY(vfi_normalize_l2(en.data(), n_e, d, VFI_MEM_HOST, device, stream));
+  // one scratch index per (device, d), kept between calls (the experiment scripts call this once per question): emptied and
+  // refilled instead of created and destroyed
+  static std::mutex cache_mu;
+  static std::vector<std::pair<std::pair<int, int>, vfi_index_t*>> cache;
+  std::lock_guard<std::mutex> cache_lock(cache_mu);
   vfi_index_t* idx = nullptr;
-  VFI_TRY(vfi_index_create(d, VFI_STORE_F32, device, &idx));
+  for (auto& ent : cache)
+    if (ent.first.first == device && ent.first.second == d) idx = ent.second;
+  if (idx == nullptr) {
+    VFI_TRY(vfi_index_create(d, VFI_STORE_F32, device, &idx));
+    cache.push_back({{device, d}, idx});
+  }
+  {
+    std::unique_lock<std::shared_mutex> lock(idx->rw);
+    DeviceGuard guard(device);
+    idx->n = 0;                                        // rows are overwritten by the add below
+    cudaMemset(idx->xnorm_bits, 0, 4);
+  }
   int rc = vfi_index_add(idx, cn.data(), n_c, VFI_MEM_HOST, stream);
   if (rc == VFI_OK) rc = vfi_index_search(idx, en.data(), n_e, k, out_scores, out_ids, VFI_MEM_HOST, stream);
-  vfi_index_destroy(idx);
   if (rc != VFI_OK) return rc;
   for (int64_t i = 0; i < n_e * k; ++i)
     if (out_ids[i] >= 0) out_ids[i] = n_c - 1 - out_ids[i];

@@ -77,20 +77,21 @@ __global__ void prep_rows_kernel(const InT* __restrict__ x, int64_t n, int d, in
 // BF16 mode: canon = bf16(q) as fp32, gemm = bf16(q).  F32: canon = q, gemm = [hi | hi | lo].
 // eps = acc_c * kp * 2^-24 * |q| * xnorm_max  (+ split_c * |q| * xnorm_max in F32 mode)
 // ------------------------------------------------------------------------------------------
-template <bool SPLIT>
-__global__ void prep_queries_kernel(const float* __restrict__ q, int nq, int d, int dp,
+template <bool SPLIT, typename InT>
+__global__ void prep_queries_kernel(const InT* __restrict__ q, int nq, int d, int dp,
                                     float* __restrict__ canon, uint16_t* __restrict__ g, int64_t kp,
                                     const uint32_t* __restrict__ xnorm_max_bits,
                                     float* __restrict__ eps) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
   if (row >= nq) return;
-  const float* qr = q + static_cast<int64_t>(row) * d;
+  const InT* qr = q + static_cast<int64_t>(row) * d;
   uint16_t* gr = g + static_cast<int64_t>(row) * kp;
   float* cr = canon + static_cast<int64_t>(row) * dp;
   double ss = 0.0;
   for (int j = lane; j < dp; j += 32) {
-    const float v = (j < d) ? qr[j] : 0.f;
+    float v = 0.f;
+    if (j < d) v = (sizeof(InT) == 2) ? bf16_to_f32(static_cast<uint16_t>(qr[j])) : static_cast<float>(qr[j]);
     const uint16_t hi = f32_to_bf16_rn(v);
     if (SPLIT) {
       const uint16_t lo = f32_to_bf16_rn(v - bf16_to_f32(hi));

@@ -83,19 +83,23 @@ class DenseIndex:
         else:
             raise ValueError("add: dtype must be float32 or bfloat16")
 
+    @staticmethod
+    def _q_dtype(q: torch.Tensor) -> int:
+        return N.DTYPE_BF16 if q.dtype == torch.bfloat16 else N.DTYPE_F32
+
     def search_batch(self, q: torch.Tensor, k: int):
-        """q: float32 [B,d] on this index's GPU.  Returns (ids int64 [B,k], scores float32 [B,k]) on the GPU."""
-        if not (isinstance(q, torch.Tensor) and q.is_cuda and q.dtype == torch.float32 and q.dim() == 2
+        """q: float32 or bfloat16 [B,d] on this index's GPU.  Returns (ids int64 [B,k], scores float32 [B,k]) on the GPU."""
+        if not (isinstance(q, torch.Tensor) and q.is_cuda and q.dtype in (torch.float32, torch.bfloat16) and q.dim() == 2
                 and q.shape[1] == self.d):
-            raise ValueError("search_batch: need a float32 [B, d] cuda tensor")
+            raise ValueError("search_batch: need a float32 or bfloat16 [B, d] cuda tensor")
         q = q.contiguous()
         B = q.shape[0]
         ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
         scores = torch.empty((B, k), dtype=torch.float32, device=self.device)
         if B:
-            N.check(N.load().vfi_index_search(self._h, C.c_void_p(q.data_ptr()), B, int(k),
-                                              C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()),
-                                              N.MEM_DEVICE, _stream_ptr(self.device)))
+            N.check(N.load().vfi_index_search_ex(self._h, C.c_void_p(q.data_ptr()), self._q_dtype(q), B, int(k),
+                                                 C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()),
+                                                 N.MEM_DEVICE, _stream_ptr(self.device)))
         return ids, scores
 
     def search_begin(self, q: torch.Tensor, k: int, out=None) -> "SearchTicket":
@@ -103,9 +107,9 @@ class DenseIndex:
         (ids, scores).  Beginning batch i+1 before finishing batch i keeps the GPU busy while the host looks at the
         certificate flag of batch i (vfi_index_search_begin / vfi_index_search_finish).  out: optional contiguous
         (ids int64 [B,k], scores float32 [B,k]) tensors to write into."""
-        if not (isinstance(q, torch.Tensor) and q.is_cuda and q.dtype == torch.float32 and q.dim() == 2
+        if not (isinstance(q, torch.Tensor) and q.is_cuda and q.dtype in (torch.float32, torch.bfloat16) and q.dim() == 2
                 and q.shape[1] == self.d and q.shape[0] > 0):
-            raise ValueError("search_begin: need a non-empty float32 [B, d] cuda tensor")
+            raise ValueError("search_begin: need a non-empty float32 or bfloat16 [B, d] cuda tensor")
         q = q.contiguous()
         B = q.shape[0]
         if out is None:
@@ -117,8 +121,9 @@ class DenseIndex:
                     and ids.dtype == torch.int64 and scores.dtype == torch.float32):
                 raise ValueError("search_begin: out must be contiguous (int64 [B,k], float32 [B,k])")
         t = C.c_int(-1)
-        N.check(N.load().vfi_index_search_begin(self._h, C.c_void_p(q.data_ptr()), B, int(k), C.c_void_p(scores.data_ptr()),
-                                                C.c_void_p(ids.data_ptr()), _stream_ptr(self.device), C.byref(t)))
+        N.check(N.load().vfi_index_search_begin_ex(self._h, C.c_void_p(q.data_ptr()), self._q_dtype(q), B, int(k),
+                                                   C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()),
+                                                   _stream_ptr(self.device), C.byref(t)))
         return SearchTicket(t.value, q, ids, scores)
 
     def search_finish(self, ticket: "SearchTicket"):
