@@ -96,13 +96,28 @@ struct GemvAttr {
 };
 template <typename RowT, int NQ>
 struct ExactAttr {
-  static void run() { cudaFuncSetAttribute(vfi::exact_scores_kernel<RowT, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kExSmemBudget); }
+  static void run() {
+    cudaFuncSetAttribute(vfi::exact_scores_kernel<RowT, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kExSmemBudget);
+    constexpr int kPref = vfi::exact_pref_threads(NQ);
+    if (kPref != vfi::kExThreads)
+      cudaFuncSetAttribute(vfi::exact_scores_kernel<RowT, NQ, kPref>, cudaFuncAttributeMaxDynamicSharedMemorySize, vfi::kExSmemBudget);
+  }
 };
 template <typename RowT, int NQ>
 struct ExactLaunch {
-  static void run(int grid, size_t smem, cudaStream_t st, const RowT* rows, int64_t pitch, int dp, int64_t n, const float* qcanon,
+  static void run(int num_sms, cudaStream_t st, const RowT* rows, int64_t pitch, int dp, int64_t n, const float* qcanon,
                   const int* qsel, int q0, float* scores, int64_t ld) {
-    vfi::exact_scores_kernel<RowT, NQ><<<grid, vfi::kExThreads, smem, st>>>(rows, pitch, dp, n, qcanon, qsel, q0, scores, ld);
+    constexpr int kPref = vfi::exact_pref_threads(NQ);
+    // more warps per SM for small groups when the queries and the row tiles still fit shared memory
+    if (kPref != vfi::kExThreads && vfi::exact_smem_bytes(dp, NQ, kPref) <= static_cast<size_t>(vfi::kExSmemBudget)) {
+      const int grid = static_cast<int>(std::min<int64_t>(num_sms, ceil_div(n, kPref)));
+      vfi::exact_scores_kernel<RowT, NQ, kPref><<<grid, kPref, vfi::exact_smem_bytes(dp, NQ, kPref), st>>>(rows, pitch, dp, n, qcanon, qsel,
+                                                                                                          q0, scores, ld);
+    } else {
+      const int grid = static_cast<int>(std::min<int64_t>(num_sms, ceil_div(n, vfi::kExThreads)));
+      vfi::exact_scores_kernel<RowT, NQ><<<grid, vfi::kExThreads, vfi::exact_smem_bytes(dp, NQ), st>>>(rows, pitch, dp, n, qcanon, qsel, q0,
+                                                                                                      scores, ld);
+    }
   }
 };
 
@@ -521,13 +536,11 @@ int exact_pass(vfi_index* idx, Workspace* ws, const int* qsel_dev, int nsel, int
     const int ng = std::min(group, nsel - s0);
     float* scores = ws->ex_scores.as<float>();
     if (n > 0) {
-      const int grid = static_cast<int>(std::min<int64_t>(idx->num_sms, ceil_div(n, 32 * (vfi::kExThreads / 32))));
-      const size_t smem = vfi::exact_smem_bytes(idx->dp, ng);
       if (idx->store == VFI_STORE_F32)
-        dispatch_nq<ExactLaunch, float>(ng, grid, smem, st, idx->master, static_cast<int64_t>(idx->dp), idx->dp, n, ws->qcanon.as<float>(),
+        dispatch_nq<ExactLaunch, float>(ng, idx->num_sms, st, idx->master, static_cast<int64_t>(idx->dp), idx->dp, n, ws->qcanon.as<float>(),
                                         qsel_dev, s0, scores, ld);
       else
-        dispatch_nq<ExactLaunch, uint16_t>(ng, grid, smem, st, idx->g, idx->kp, idx->dp, n, ws->qcanon.as<float>(), qsel_dev, s0, scores, ld);
+        dispatch_nq<ExactLaunch, uint16_t>(ng, idx->num_sms, st, idx->g, idx->kp, idx->dp, n, ws->qcanon.as<float>(), qsel_dev, s0, scores, ld);
       LAUNCHED();
       VFI_CUDA(cudaGetLastError());
     }

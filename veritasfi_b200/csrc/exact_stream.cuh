@@ -29,14 +29,14 @@
 
 namespace vfi {
 
-constexpr int kExThreads = 512;                 // 16 warps, one row per thread per step
+constexpr int kExThreads = 512;                 // 16 warps, one row per thread per step (the base configuration)
 constexpr int kExMaxQ = 8;                      // queries per pass over the corpus
 constexpr int kExPiece = 256;                   // bytes per bulk copy
 constexpr int kExPitch = kExPiece + 16;         // conflict-free 128-bit reads of 32 different rows
 constexpr int kExTileBytes = (kExThreads / 32) * 32 * kExPitch;
 constexpr int kExSmemBudget = 227 * 1024 - 1024;
-__host__ __device__ inline size_t exact_smem_bytes(int dp, int nq) {
-  return static_cast<size_t>(nq) * dp * 8 + (kExThreads / 32) * 8 + kExTileBytes;
+__host__ __device__ inline size_t exact_smem_bytes(int dp, int nq, int threads = kExThreads) {
+  return static_cast<size_t>(nq) * dp * 8 + (threads / 32) * 8 + static_cast<size_t>(threads / 32) * 32 * kExPitch;
 }
 // largest query group whose fp64 copies fit beside the row tiles
 inline int exact_max_group(int dp) {
@@ -44,21 +44,25 @@ inline int exact_max_group(int dp) {
   const int g = static_cast<int>(room / (static_cast<int64_t>(dp) * 8));
   return g < 1 ? 0 : (g > kExMaxQ ? kExMaxQ : g);
 }
+// The kernel is bound by how many rows an SM has in flight (one 272-byte stage per row, 16 warps: fp64 / XU / LSU pipes each
+// ~30 % busy, ncu).  Small groups need few registers and little shared memory for their queries, so they run with more
+// warps per SM when everything still fits: 24 warps for 1-2 queries, 20 for 3-4.
+__host__ __device__ constexpr int exact_pref_threads(int nq) { return nq <= 2 ? 768 : (nq <= 4 ? 640 : 512); }
 
-template <typename RowT, int NQ>
-__global__ void __launch_bounds__(kExThreads, 1) exact_scores_kernel(
+template <typename RowT, int NQ, int THREADS = kExThreads>
+__global__ void __launch_bounds__(THREADS, 1) exact_scores_kernel(
     const RowT* __restrict__ rows, int64_t row_pitch, int dp, int64_t n_rows, const float* __restrict__ qcanon,
     const int* __restrict__ qsel /* [NQ] rows of qcanon, or nullptr = q0 .. q0+NQ-1 */, int q0,
     float* __restrict__ scores_out /* [NQ][ld] */, int64_t ld) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   double* qd = reinterpret_cast<double*>(smem_raw);                       // [NQ][dp]
   uint64_t* bars = reinterpret_cast<uint64_t*>(qd + static_cast<size_t>(NQ) * dp);   // one per warp
-  uint8_t* tiles = reinterpret_cast<uint8_t*>(bars + kExThreads / 32);
+  uint8_t* tiles = reinterpret_cast<uint8_t*>(bars + THREADS / 32);
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int j = 0; j < NQ; ++j) {
     const int q = (qsel != nullptr) ? qsel[q0 + j] : q0 + j;
     const float* qv = qcanon + static_cast<int64_t>(q) * dp;
-    for (int e = tid; e < dp; e += kExThreads) qd[j * dp + e] = static_cast<double>(qv[e]);
+    for (int e = tid; e < dp; e += THREADS) qd[j * dp + e] = static_cast<double>(qv[e]);
   }
   uint64_t* bar = &bars[warp];
   if (lane == 0) {
@@ -72,8 +76,8 @@ __global__ void __launch_bounds__(kExThreads, 1) exact_scores_kernel(
   uint8_t* my_tile = tiles + (static_cast<size_t>(warp) * 32 + lane) * kExPitch;
   const int64_t n_groups = (n_rows + 31) / 32;
   uint32_t phase = 0;
-  for (int64_t g = static_cast<int64_t>(blockIdx.x) * (kExThreads / 32) + warp; g < n_groups;
-       g += static_cast<int64_t>(gridDim.x) * (kExThreads / 32)) {
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * (THREADS / 32) + warp; g < n_groups;
+       g += static_cast<int64_t>(gridDim.x) * (THREADS / 32)) {
     const int64_t row = g * 32 + lane;
     const bool valid = row < n_rows;
     const uint32_t n_valid = __popc(__ballot_sync(0xFFFFFFFFu, valid));
