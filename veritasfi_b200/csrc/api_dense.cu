@@ -134,9 +134,11 @@ struct Workspace {
   DevBuf qin, qcanon, qg, eps, cand, cand_count, keys, keys_n, bound, keys2, flag, out_scores, out_ids, dbg, sel, tau,
       ex_scores, ex_state, ex_keys;
   int* h_flag = nullptr;         // pinned: number of queries of the batch whose certificate failed
+  int* h_flag_dev = nullptr;     // the same word as the device sees it (written by the last CTA of the tail)
   cudaEvent_t done = nullptr;    // recorded behind the flag copy
   cudaEvent_t pev[4] = {nullptr, nullptr, nullptr, nullptr};   // VFI_OPT_PROFILE: around the dominant kernel [0,1] and the tail [2,3]
   cudaStream_t own = nullptr;    // host-buffer calls that pass no stream run here, so concurrent callers overlap
+  cudaEvent_t tev[10] = {};      // VFI_TRACE_STEPS=1 (debugging aid): one event behind every stream operation of a batch
   // batch state
   bool needs_check = false, used_tau = false, profiled = false;
   const void* q = nullptr;
@@ -148,7 +150,8 @@ struct Workspace {
   int ticket = -1;
 
   int init() {
-    VFI_CUDA(cudaMallocHost(&h_flag, sizeof(int) * 4));
+    VFI_CUDA(cudaHostAlloc(&h_flag, sizeof(int) * 4, cudaHostAllocMapped | cudaHostAllocPortable));
+    VFI_CUDA(cudaHostGetDevicePointer(&h_flag_dev, h_flag, 0));
     VFI_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
     for (cudaEvent_t& e : pev) VFI_CUDA(cudaEventCreate(&e));
     VFI_CUDA(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
@@ -163,8 +166,20 @@ struct Workspace {
     for (cudaEvent_t e : pev)
       if (e) cudaEventDestroy(e);
     if (own) cudaStreamDestroy(own);
+    for (cudaEvent_t e : tev)
+      if (e) cudaEventDestroy(e);
   }
 };
+
+// VFI_TRACE_STEPS=1: where the device time of one batch goes, operation by operation (gaps included), on stderr
+const bool g_trace_steps = std::getenv("VFI_TRACE_STEPS") != nullptr;
+cudaEvent_t g_trace_epoch = nullptr;
+inline void trace_mark(Workspace* ws, int i, cudaStream_t st) {
+  if (!g_trace_steps) return;
+  if (!g_trace_epoch) { cudaEventCreate(&g_trace_epoch); cudaEventRecord(g_trace_epoch, st); }
+  if (!ws->tev[i]) cudaEventCreate(&ws->tev[i]);
+  cudaEventRecord(ws->tev[i], st);
+}
 
 }  // namespace
 
@@ -489,7 +504,8 @@ bool gemv_ok(const vfi_index* idx) {
   return bytes <= vfi::kGemvMaxVec * 32 * 16;
 }
 
-int prep_queries(vfi_index* idx, Workspace* ws, const void* q_dev, int q_dtype, int nq, cudaStream_t st) {
+int prep_queries(vfi_index* idx, Workspace* ws, const void* q_dev, int q_dtype, int nq, cudaStream_t st, int* zero_a = nullptr,
+                 int* zero_b = nullptr) {
   VFI_TRY(ws->qcanon.ensure(static_cast<size_t>(nq) * idx->dp * 4));
   VFI_TRY(ws->qg.ensure(static_cast<size_t>(nq) * idx->kp * 2));
   VFI_TRY(ws->eps.ensure(static_cast<size_t>(nq) * 4));
@@ -501,12 +517,12 @@ int prep_queries(vfi_index* idx, Workspace* ws, const void* q_dev, int q_dtype, 
   const bool split = idx->store == VFI_STORE_F32;
   if (q_dtype == VFI_DTYPE_BF16) {
     const uint16_t* q = static_cast<const uint16_t*>(q_dev);
-    if (split) vfi::prep_queries_kernel<true, uint16_t><<<blocks, threads, 0, st>>>(q, nq, idx->d, idx->dp, canon, qg, idx->kp, idx->xnorm_bits, eps);
-    else vfi::prep_queries_kernel<false, uint16_t><<<blocks, threads, 0, st>>>(q, nq, idx->d, idx->dp, canon, qg, idx->kp, idx->xnorm_bits, eps);
+    if (split) vfi::prep_queries_kernel<true, uint16_t><<<blocks, threads, 0, st>>>(q, nq, idx->d, idx->dp, canon, qg, idx->kp, idx->xnorm_bits, eps, zero_a, zero_b);
+    else vfi::prep_queries_kernel<false, uint16_t><<<blocks, threads, 0, st>>>(q, nq, idx->d, idx->dp, canon, qg, idx->kp, idx->xnorm_bits, eps, zero_a, zero_b);
   } else {
     const float* q = static_cast<const float*>(q_dev);
-    if (split) vfi::prep_queries_kernel<true, float><<<blocks, threads, 0, st>>>(q, nq, idx->d, idx->dp, canon, qg, idx->kp, idx->xnorm_bits, eps);
-    else vfi::prep_queries_kernel<false, float><<<blocks, threads, 0, st>>>(q, nq, idx->d, idx->dp, canon, qg, idx->kp, idx->xnorm_bits, eps);
+    if (split) vfi::prep_queries_kernel<true, float><<<blocks, threads, 0, st>>>(q, nq, idx->d, idx->dp, canon, qg, idx->kp, idx->xnorm_bits, eps, zero_a, zero_b);
+    else vfi::prep_queries_kernel<false, float><<<blocks, threads, 0, st>>>(q, nq, idx->d, idx->dp, canon, qg, idx->kp, idx->xnorm_bits, eps, zero_a, zero_b);
   }
   LAUNCHED();
   VFI_CUDA(cudaGetLastError());
@@ -705,10 +721,15 @@ int search_launch(vfi_index* idx, Workspace* ws, const void* q_dev, int q_dtype,
   ws->o_scores = out_scores;
   ws->o_ids = out_ids;
   ws->st = st;
-  VFI_TRY(prep_queries(idx, ws, q_dev, q_dtype, nq, st));
-  VFI_TRY(ws->flag.ensure(static_cast<size_t>(kMaxQueriesPerLaunch + 1) * 4));
-  int* d_flag = ws->flag.as<int>();   // [0] number of queries whose certificate failed, [1..] those queries
-  VFI_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
+  trace_mark(ws, 0, st);
+  VFI_TRY(ws->flag.ensure(static_cast<size_t>(kMaxQueriesPerLaunch + 2) * 4));
+  // [0] number of queries whose certificate failed, [1..1024] those queries, [1025] finished CTAs of the last tail kernel;
+  // both counters are zeroed by the query preparation kernel, and the count reaches the host without a copy operation
+  // (publish_flag_count)
+  int* d_flag = ws->flag.as<int>();
+  int* d_done = d_flag + kMaxQueriesPerLaunch + 1;
+  VFI_TRY(prep_queries(idx, ws, q_dev, q_dtype, nq, st, d_flag, d_done));
+  trace_mark(ws, 1, st);
   const int64_t n = idx->n;
   int keep = idx->opt_overfetch > 0 ? static_cast<int>(idx->opt_overfetch)
                                     : static_cast<int>(round_up(k + std::max(16, k / 4), 32));
@@ -778,11 +799,13 @@ int search_launch(vfi_index* idx, Workspace* ws, const void* q_dev, int q_dtype,
       VFI_TRY(ws->tau.ensure(static_cast<size_t>(nq) * 4));
       VFI_TRY(launch_fused(idx, ws, nq, 32, full ? vfi::MODE_STORE : vfi::MODE_CHUNKMAX, ws->dbg.as<float>(), ld, nullptr, nullptr,
                            nullptr, nullptr, st, rr, rs, false));
-      vfi::tau_from_scores_kernel<<<nq, 256, sizeof(vfi::SelectSmem), st>>>(ws->dbg.as<float>(), ld, static_cast<int>(n_vals), m,
-                                                                           ws->tau.as<float>(), idx->opt_tau_hint == 2 ? 1 : 0);
+      trace_mark(ws, 3, st);
+      vfi::tau_from_scores_kernel<<<static_cast<unsigned>(ceil_div(nq, vfi::kTauWarps)), vfi::kTauWarps * 32, 0, st>>>(
+          ws->dbg.as<float>(), ld, static_cast<int>(n_vals), nq, m, ws->tau.as<float>(), idx->opt_tau_hint == 2 ? 1 : 0);
       LAUNCHED();
       VFI_CUDA(cudaGetLastError());
       tau = ws->tau.as<float>();
+      trace_mark(ws, 4, st);
     }
   }
   if (path == 2 && small_ok(idx, nq)) {
@@ -816,6 +839,7 @@ int search_launch(vfi_index* idx, Workspace* ws, const void* q_dev, int q_dtype,
     if (prof) cudaEventRecord(ws->pev[1], st);
     VFI_CUDA(cudaGetLastError());
   }
+  trace_mark(ws, 5, st);
   const bool tail_prof = idx->opt_profile != 0;
   if (tail_prof) cudaEventRecord(ws->pev[2], st);
   VFI_TRY(ws->keys.ensure(static_cast<size_t>(nq) * keep * 8));
@@ -834,6 +858,7 @@ int search_launch(vfi_index* idx, Workspace* ws, const void* q_dev, int q_dtype,
         ws->keys_n.as<uint32_t>(), ws->bound.as<float>());
   LAUNCHED();
   VFI_CUDA(cudaGetLastError());
+  trace_mark(ws, 6, st);
   if (keep <= 256 && idx->dp <= vfi::kRfMaxDp) {
     // K2: one thread per candidate: rescoring + final order + certificate
     const int threads = static_cast<int>(round_up(keep, 32));
@@ -842,11 +867,12 @@ int search_launch(vfi_index* idx, Workspace* ws, const void* q_dev, int q_dtype,
       vfi::rescore_finalize_kernel<float, 256, 1><<<nq, threads, smem, st>>>(
           ws->keys.as<uint64_t>(), ws->keys_n.as<uint32_t>(), ws->bound.as<float>(), keep, idx->master, static_cast<int64_t>(idx->dp),
           static_cast<int>(idx->dp), ws->qcanon.as<float>(), k, idx->id_offset, ws->eps.as<float>(), out_scores, out_ids, d_flag + 1,
-          d_flag, idx->d_max_err);
+          d_flag, idx->d_max_err, d_done, ws->h_flag_dev);
     else
       vfi::rescore_finalize_kernel<uint16_t, 256, 1><<<nq, threads, smem, st>>>(
           ws->keys.as<uint64_t>(), ws->keys_n.as<uint32_t>(), ws->bound.as<float>(), keep, idx->g, idx->kp, static_cast<int>(idx->dp),
-          ws->qcanon.as<float>(), k, idx->id_offset, ws->eps.as<float>(), out_scores, out_ids, d_flag + 1, d_flag, idx->d_max_err);
+          ws->qcanon.as<float>(), k, idx->id_offset, ws->eps.as<float>(), out_scores, out_ids, d_flag + 1, d_flag, idx->d_max_err,
+          d_done, ws->h_flag_dev);
     LAUNCHED();
     VFI_CUDA(cudaGetLastError());
   } else {
@@ -865,12 +891,14 @@ int search_launch(vfi_index* idx, Workspace* ws, const void* q_dev, int q_dtype,
     VFI_CUDA(cudaGetLastError());
     vfi::finalize_kernel<1><<<nq, 256, sizeof(vfi::SelectSmem), st>>>(ws->keys2.as<uint64_t>(), keep, keep, nullptr,
                                                                      ws->keys_n.as<uint32_t>(), k, idx->id_offset, ws->bound.as<float>(),
-                                                                     ws->eps.as<float>(), out_scores, out_ids, d_flag + 1, d_flag);
+                                                                     ws->eps.as<float>(), out_scores, out_ids, d_flag + 1, d_flag,
+                                                                     d_done, ws->h_flag_dev);
     LAUNCHED();
     VFI_CUDA(cudaGetLastError());
   }
+  trace_mark(ws, 7, st);
   if (tail_prof) cudaEventRecord(ws->pev[3], st);
-  VFI_CUDA(cudaMemcpyAsync(ws->h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+  trace_mark(ws, 8, st);
   VFI_CUDA(cudaEventRecord(ws->done, st));
   ws->needs_check = true;
   ws->used_tau = tau != nullptr;
@@ -888,6 +916,25 @@ void note_launch(vfi_index* idx, const LaunchInfo& info) {
 // hint is redone without it, queries whose candidates tie across the cut are re-run by the exact streaming pass.
 int search_finish(vfi_index* idx, Workspace* ws) {
   VFI_CUDA(cudaEventSynchronize(ws->done));
+  if (g_trace_steps && ws->needs_check && ws->tev[8]) {
+    static const char* names[9] = {"start", "prep", "-", "sample", "tau", "K1", "cand_reduce", "rescore", "-"};
+    float t0 = 0.f;
+    cudaEventElapsedTime(&t0, g_trace_epoch, ws->tev[0]);
+    std::string line = "[vfi steps] start at " + std::to_string(t0) + " ms:";
+    cudaEvent_t prev = ws->tev[0];
+    for (int i = 1; i < 9; ++i) {
+      if (!ws->tev[i]) continue;
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, prev, ws->tev[i]) != cudaSuccess) { cudaGetLastError(); continue; }
+      char buf[64];
+      std::snprintf(buf, sizeof buf, " %s %.1f us;", names[i], ms * 1e3f);
+      line += buf;
+      prev = ws->tev[i];
+    }
+    float tot = 0.f;
+    cudaEventElapsedTime(&tot, ws->tev[0], ws->tev[8]);
+    std::fprintf(stderr, "%s total %.1f us\n", line.c_str(), tot * 1e3f);
+  }
   if (ws->profiled) {
     float ms_k = 0.f, ms_t = 0.f;
     const bool ok_k = cudaEventElapsedTime(&ms_k, ws->pev[0], ws->pev[1]) == cudaSuccess;

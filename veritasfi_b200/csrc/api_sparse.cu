@@ -408,7 +408,7 @@ int vfi_bm25_search(vfi_bm25_t* b, const int32_t* q_tokens, const int64_t* q_ind
     LAUNCHED();
     vfi::finalize_kernel<0><<<static_cast<unsigned>(nq), 256, sizeof(vfi::SelectSmem), st>>>(
         w->keys.as<uint64_t>(), keep, keep, nullptr, w->keys_n.as<uint32_t>(), k, b->id_offset, nullptr, nullptr, d_scores, d_ids,
-        nullptr, nullptr);
+        nullptr, nullptr, nullptr, nullptr);
     LAUNCHED();
     if (b->all_positive) {
       vfi::bm25_zero_fill_kernel<<<static_cast<unsigned>(ceil_div(nq, 4)), 128, 0, st>>>(d_scores, d_ids, static_cast<int>(nq), k,

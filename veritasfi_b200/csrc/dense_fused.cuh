@@ -305,6 +305,11 @@ dense_fused_kernel(const __grid_constant__ CUtensorMap tmap_q,
 // Every SM pair of the chip is busy for any batch size.  Per-query selection state (count, threshold) lives in
 // shared memory between the visits of a query tile.
 //
+// Measured and not kept (round 2, profiles/r2_ncu_summary.md): a TMA L2 prefetch (cp.async.bulk.prefetch.tensor) of the pair's
+// next corpus tile during the last visit of the current one — 1-2 % slower at C3, 6-10 % slower at C2 (the prefetches compete
+// with the demand loads of an HBM-co-limited launch); a ring of 5 / 4 / 3 stages instead of 6 — 5 / 5 / 8 % slower on a 1/8
+// shard of C3 at full clocks (no difference under the power cap at C3): the kernel is fill-latency-bound at 1.97 GHz.
+//
 // Barriers: full[s] lives in the leader and counts the TMA bytes of BOTH CTAs; empty[s] and tfull[a] exist in both
 // CTAs and are signalled by one multicast tcgen05.commit; tempty[a] lives in the leader and collects the 8 epilogue
 // warps of the pair (the peer's arrive remotely).

@@ -9,7 +9,8 @@
 namespace vfi {
 
 // ------------------------------------------------------------------------------------------
-// K1c: union of the per-group candidate buffers of one query -> the k' best keys, sorted.
+// K1c: union of the per-group candidate buffers of one query -> the k' best keys, in no particular order (every consumer
+// rescoring or ordering them itself) unless the union exceeds the shared-memory buffer (then sorted descending).
 // bound[q] = an upper bound on the tensor-core score of every row that is NOT in the output:
 //   the k'-th key's score when at least k' rows were admitted, else the admission hint (rows at
 //   or below the hint were never admitted), else -inf (every row of the shard is a candidate).
@@ -78,6 +79,36 @@ __global__ void __launch_bounds__(256, (sizeof(SM) <= 16384 ? 7 : 4)) cand_reduc
   __syncthreads();
   const uint32_t total = s_pref[n_groups];
   GroupBufSrc src{cand, s_pref, n_groups, nq_pad, cap, q};
+  if (total <= SM::kCap) {
+    // the consumers (K2 rescoring, K2a) take the k' best in any order: stage the keys once, find the k'-th largest by a
+    // radix walk and emit what is at or above it — no sort (round 2: 58 -> ~25 us for 1024 queries of ~700 keys)
+    if (threadIdx.x == 0) sm->ctr = 0;
+    __syncthreads();
+    src.for_each([&](uint64_t key) {
+      if (key != 0ull) sm->keys[atomicAdd(&sm->ctr, 1u)] = key;
+    });
+    __syncthreads();
+    const uint32_t n_keys = sm->ctr;
+    const uint64_t kth = block_kth_key_smem(sm, n_keys, static_cast<uint32_t>(keep));
+    if (threadIdx.x == 0) sm->ctr = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_keys; i += blockDim.x) {
+      const uint64_t key = sm->keys[i];
+      if (key >= kth) out_keys[static_cast<size_t>(q) * keep + atomicAdd(&sm->ctr, 1u)] = key;
+    }
+    __syncthreads();
+    const uint32_t n = sm->ctr;                     // min(n_keys, keep)
+    for (uint32_t i = n + threadIdx.x; i < static_cast<uint32_t>(keep); i += blockDim.x)
+      out_keys[static_cast<size_t>(q) * keep + i] = kKeyNone;
+    if (threadIdx.x == 0) {
+      out_n[q] = n;
+      float b;
+      if (n_keys >= static_cast<uint32_t>(keep)) b = key_score(kth);
+      else b = (tau_init != nullptr) ? tau_init[q] : -INFINITY;
+      bound[q] = b;
+    }
+    return;
+  }
   const uint32_t n = block_topk(src, total, static_cast<uint32_t>(keep), sm);
   for (uint32_t i = threadIdx.x; i < static_cast<uint32_t>(keep); i += blockDim.x)
     out_keys[static_cast<size_t>(q) * keep + i] = (i < n) ? sm->keys[i] : kKeyNone;
@@ -114,7 +145,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(
     const int* __restrict__ qsel, const uint32_t* __restrict__ n_cand, int k, int64_t id_offset,
     const float* __restrict__ bound, const float* __restrict__ eps,
     float* __restrict__ out_scores, int64_t* __restrict__ out_ids, int* __restrict__ flagged,
-    int* __restrict__ n_flagged) {
+    int* __restrict__ n_flagged, int* __restrict__ done_ctas, int* __restrict__ host_n_flagged) {
   extern __shared__ uint8_t smem_raw[];
   SelectSmem* sm = reinterpret_cast<SelectSmem*>(smem_raw);
   const int qslot = blockIdx.x;
@@ -140,6 +171,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(
   } else if (threadIdx.x == 0) {
     flagged[atomicAdd(n_flagged, 1)] = q;
   }
+  if (CHECK) publish_flag_count(n_flagged, done_ctas, host_n_flagged);
 }
 
 }  // namespace vfi

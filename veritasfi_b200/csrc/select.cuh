@@ -144,6 +144,60 @@ __device__ inline bool merge_sorted_rows(const uint64_t* keys, int rows, int k, 
   return ok;
 }
 
+// Selection WITHOUT ordering among the n distinct non-zero keys staged in sm->keys[0..n), n <= SM::kCap: returns the k-th
+// largest key (the smallest of the k best) — the keys >= it are exactly the k best — or 0 when n < k (every key is kept).
+// MSD radix walk over 8-bit digits of the 64-bit keys, histogram in shared memory with warp-aggregated atomics (the keys
+// of one query share their leading bytes, so plain atomics would serialise on one bin).  Three barriers per pass and at
+// most 8 passes (typically 3-4: the walk stops as soon as a bin holds exactly the keys still wanted), against the 55
+// barrier-separated stages of a 1024-key bitonic sort.  blockDim.x must be a multiple of 32, >= 64.  All threads must call.
+template <class SM>
+__device__ __forceinline__ uint64_t block_kth_key_smem(SM* sm, uint32_t n, uint32_t k) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+  if (n < k) return 0ull;
+  uint64_t prefix = 0;
+  uint32_t remaining = k;
+  for (int shift = 56; shift >= 0 && n > k; shift -= 8) {
+    for (uint32_t i = tid; i < 256; i += blockDim.x) sm->hist[i] = 0;
+    __syncthreads();
+    const uint64_t himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
+    for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {     // warp-uniform trip count: every lane takes part in the match
+      const uint32_t i = i0 + tid;
+      uint32_t digit = 0xFFFFFFFFu;
+      if (i < n) {
+        const uint64_t key = sm->keys[i];
+        if ((key & himask) == prefix) digit = static_cast<uint32_t>(key >> shift) & 0xFFu;
+      }
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, digit);
+      if (digit != 0xFFFFFFFFu && lane == static_cast<uint32_t>(__ffs(peers) - 1)) atomicAdd(&sm->hist[digit], __popc(peers));
+    }
+    __syncthreads();
+    if (tid < 32) hist_find_bin(sm->hist, remaining, tid, &sm->digit, &sm->before, &sm->cnt, &sm->seen);
+    __syncthreads();
+    prefix |= static_cast<uint64_t>(sm->digit) << shift;
+    remaining -= sm->before;
+    const bool stop = (sm->cnt == remaining) || shift == 0;
+    __syncthreads();
+    if (stop) break;
+  }
+  // every key >= prefix is kept; the k-th largest is the smallest of them
+  __shared__ unsigned long long s_min;
+  if (tid == 0) s_min = ~0ull;
+  __syncthreads();
+  unsigned long long mn = ~0ull;
+  for (uint32_t i = tid; i < n; i += blockDim.x) {
+    const uint64_t key = sm->keys[i];
+    if (key >= prefix && key < mn) mn = key;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xFFFFFFFFu, mn, o);
+    mn = t < mn ? t : mn;
+  }
+  if (lane == 0 && mn != ~0ull) atomicMin(&s_min, mn);
+  __syncthreads();
+  return s_min;
+}
+
 // Src: struct with   template<class F> __device__ void for_each(F f) const
 // calling f(key) for the keys assigned to this thread (each key visited by exactly one thread).
 // Leaves the min(total,k) best keys sorted descending in sm->keys[0..); returns that count.

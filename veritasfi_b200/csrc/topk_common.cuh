@@ -152,5 +152,19 @@ __device__ __forceinline__ void block_bitonic_desc(uint64_t* keys, uint32_t n) {
   __syncthreads();
 }
 
+// The last CTA of a grid to get here copies *counter to *host_out (pinned host memory mapped into the device address
+// space): the host reads the batch's certificate count after the event behind the kernel without a copy operation in the
+// stream (a 4-byte cudaMemcpyAsync costs the stream 8-15 us on B200, the kernel epilogue nothing measurable).  Thread 0
+// of every CTA must be the thread that updated *counter.  done_ctas starts at zero (prep_queries_kernel).
+__device__ __forceinline__ void publish_flag_count(int* counter, int* done_ctas, int* host_out) {
+  if (done_ctas == nullptr || threadIdx.x != 0) return;
+  __threadfence();
+  if (atomicAdd(done_ctas, 1) == static_cast<int>(gridDim.x * gridDim.y) - 1) {
+    __threadfence();
+    *reinterpret_cast<volatile int*>(host_out) = *reinterpret_cast<volatile int*>(counter);
+    __threadfence_system();
+  }
+}
+
 #endif  // __CUDACC__
 }  // namespace vfi
