@@ -48,6 +48,7 @@ WORKLOADS = {
                  desc="one 1/8 shard of C4 on one GPU (625k chunks, 125k titles)"),
     "c4small": dict(kind="hybrid", n=60_000, n_ts=12_000, d=256, b=64, k=20, depth=50, vocab=8192, mean_len=40, desc="smoke-size hybrid"),
     "c3s8": dict(kind="dense", n=1_250_000, d=1024, b=1024, k=100, desc="one 1/8 row shard of C3 (1.25Mx1024 bf16), 1024-query batch, top-100"),
+    "c3q": dict(kind="dense", n=2_500_000, d=1024, b=1024, k=100, desc="a quarter of C3 (2.5Mx1024 bf16; on two GPUs each shard is the 1.25M rows of an 8-GPU C3 run), 1024-query batch, top-100"),
     "b16": dict(kind="dense", n=1_000_000, d=1024, b=16, k=100, desc="1Mx1024 bf16 corpus, 16-query batch, top-100 (serving batch)"),
     "b64": dict(kind="dense", n=1_000_000, d=1024, b=64, k=100, desc="1Mx1024 bf16 corpus, 64-query batch, top-100 (serving batch)"),
     "b128": dict(kind="dense", n=1_000_000, d=1024, b=128, k=100, desc="1Mx1024 bf16 corpus, 128-query batch, top-100 (serving batch)"),

@@ -209,6 +209,19 @@ int vfi_exchange_merge(vfi_exchange_t* ex, const float* scores, const int64_t* i
 int vfi_exchange_merge_flagged(vfi_exchange_t* ex, const float* scores, const int64_t* ids, int64_t nq, int k, int k_out,
                                float* out_scores, int64_t* out_ids, const int* fail_a, const int* fail_b, int* any_fail,
                                void* stream);
+/* Compute + collective (sharded search): vfi_index_search_begin_push is vfi_index_search_begin_ex whose rescoring kernel also
+ * SENDS — the CTA that has just ordered and certified a query stores that row (global ids) into every rank's window over NVLink
+ * while the other queries are still being rescored, without waiting for the round trip (a batch on a path without that kernel
+ * is pushed by a kernel of its own behind the search: every rank consumes the epoch).  vfi_exchange_merge_pushed, enqueued behind
+ * it on the same stream, publishes the rows (fail_flag: vfi_index_ticket_flag of the batch, may be NULL = rows are final), waits
+ * for the peers' rows of that epoch and merges them; *slot names the host word that holds, once an event recorded behind the
+ * call has completed, whether ANY rank's rows were not final (vfi_exchange_any_fail) — no copy operation in the stream.  Both
+ * calls are collectives like vfi_exchange_merge. */
+int vfi_index_search_begin_push(vfi_index_t* idx, const void* q, int q_dtype, int64_t nq, int k, float* out_scores,
+                                int64_t* out_ids, vfi_exchange_t* ex, void* stream, int* ticket);
+int vfi_exchange_merge_pushed(vfi_exchange_t* ex, int64_t nq, int k, int k_out, float* out_scores, int64_t* out_ids,
+                              const int* fail_flag, int* slot, void* stream);
+int vfi_exchange_any_fail(vfi_exchange_t* ex, int slot, int* any_fail);
 int vfi_exchange_destroy(vfi_exchange_t* ex);
 
 /* ---- BM25 over token-major postings (bm25s CSC arrays) ----------------------------------- */

@@ -24,4 +24,4 @@ def test_sharded_search_on_all_visible_gpus_equals_unsharded_oracle():
            "--master-port", str(port), os.path.join(ROOT, "tools", "multi_gpu_check.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-    assert p.stdout.count("True") == 9 and "False" not in p.stdout, p.stdout[-3000:]
+    assert p.stdout.count("True") == 10 and "False" not in p.stdout, p.stdout[-3000:]

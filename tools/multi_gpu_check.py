@@ -91,6 +91,34 @@ def main():
         if s.exchange is not None:
             s.exchange.close()
         idx.close()
+    # the fused push with ranks on different local paths: the last rank scores its shard with the exact streaming scorer, whose
+    # rows are pushed by the standalone push kernel, the others send from their rescoring kernel; one epoch on every rank
+    if True:
+        n, d, nq, k = 90_000, 128, 70, 50
+        xb = synth.dense_corpus_np(n, d, 321)
+        xq = synth.dense_queries_np(nq, d, 321, xb)
+        lo, hi = shard_bounds(n, world, rank)
+        idx = DenseIndex(d, store="bf16", device=dev, id_offset=lo)
+        idx.add(xb[lo:hi])
+        idx.set_option(N.OPT_FORCE_PATH, N.PATH_EXACT if rank == world - 1 else N.PATH_FUSED)
+        D0, I0 = flat_ip.search(xq, xb, k)
+        s = make_sharded_dense(idx, exchange="peer", max_nq=nq, max_k=k)
+        q = torch.from_numpy(xq).to(dev)
+        tickets = [s.search_begin(q, k) for _ in range(3)]
+        good = True
+        for t in tickets:
+            ids, scores = s.search_finish(t)
+            torch.cuda.synchronize()
+            good &= bool((ids.cpu().numpy() == I0).all() and (scores.cpu().numpy() == D0).all())
+        good &= s.re_exchanges == 0 and all(t.pushed for t in tickets) == (s.exchange is not None)
+        flag = torch.tensor([1 if good else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"[multi-gpu G={world} fused push, last rank on the exact path] three batches in flight equal the oracle: {bool(flag.item())}", flush=True)
+        ok &= bool(flag.item())
+        if s.exchange is not None:
+            s.exchange.close()
+        idx.close()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

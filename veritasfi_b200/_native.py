@@ -93,6 +93,9 @@ _SIGNATURES = {
                                   C.c_float, C.c_int, _P, _P, C.c_int, _P]),
     "vfi_index_ticket_flag": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
     "vfi_exchange_merge_flagged": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "vfi_index_search_begin_push": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_int)]),
+    "vfi_exchange_merge_pushed": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, C.POINTER(C.c_int), _P]),
+    "vfi_exchange_any_fail": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
     "vfi_bm25_create_from": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(_P)]),
     "vfi_bm25_rank_range": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),
 }

@@ -15,6 +15,7 @@
 #include <unordered_map>
 
 #include "api_common.h"
+#include "api_exchange.h"
 #include "dense_fused.cuh"
 #include "dense_small.cuh"
 #include "dense_support.cuh"
@@ -705,12 +706,13 @@ int launch_small(vfi_index* idx, Workspace* ws, int nq, int keep, const float* t
 struct LaunchInfo {
   int path = 0, keep = 0;
   bool fused = false;
+  bool pushed = false;   // the rescoring kernel pushed the batch's rows into the peers' exchange windows
 };
 
 // Enqueue one batch of <= kMaxQueriesPerLaunch queries already on the device (results to device buffers) in workspace
 // `ws` without waiting: everything up to the copy of the certificate flag.  search_finish() waits and repairs.
 int search_launch(vfi_index* idx, Workspace* ws, const void* q_dev, int q_dtype, int nq, int k, float* out_scores, int64_t* out_ids,
-                  cudaStream_t st, bool no_hint, LaunchInfo* info) {
+                  cudaStream_t st, bool no_hint, LaunchInfo* info, const vfi::PushTarget* push = nullptr) {
   ws->needs_check = false;
   ws->used_tau = false;
   ws->profiled = false;
@@ -860,19 +862,24 @@ int search_launch(vfi_index* idx, Workspace* ws, const void* q_dev, int q_dtype,
   VFI_CUDA(cudaGetLastError());
   trace_mark(ws, 6, st);
   if (keep <= 256 && idx->dp <= vfi::kRfMaxDp) {
-    // K2: one thread per candidate: rescoring + final order + certificate
+    // K2: one thread per candidate: rescoring + final order + certificate (+ the push of a sharded batch's rows)
+    vfi::PushTarget pt{};
+    if (push != nullptr) {
+      pt = *push;
+      info->pushed = true;
+    }
     const int threads = static_cast<int>(round_up(keep, 32));
     const size_t smem = vfi::rescore_bulk_smem<256>(static_cast<int>(idx->dp), threads, 1);
     if (idx->store == VFI_STORE_F32)
       vfi::rescore_finalize_kernel<float, 256, 1><<<nq, threads, smem, st>>>(
           ws->keys.as<uint64_t>(), ws->keys_n.as<uint32_t>(), ws->bound.as<float>(), keep, idx->master, static_cast<int64_t>(idx->dp),
           static_cast<int>(idx->dp), ws->qcanon.as<float>(), k, idx->id_offset, ws->eps.as<float>(), out_scores, out_ids, d_flag + 1,
-          d_flag, idx->d_max_err, d_done, ws->h_flag_dev);
+          d_flag, idx->d_max_err, d_done, ws->h_flag_dev, pt);
     else
       vfi::rescore_finalize_kernel<uint16_t, 256, 1><<<nq, threads, smem, st>>>(
           ws->keys.as<uint64_t>(), ws->keys_n.as<uint32_t>(), ws->bound.as<float>(), keep, idx->g, idx->kp, static_cast<int>(idx->dp),
           ws->qcanon.as<float>(), k, idx->id_offset, ws->eps.as<float>(), out_scores, out_ids, d_flag + 1, d_flag, idx->d_max_err,
-          d_done, ws->h_flag_dev);
+          d_done, ws->h_flag_dev, pt);
     LAUNCHED();
     VFI_CUDA(cudaGetLastError());
   } else {
@@ -1064,6 +1071,49 @@ int vfi_index_search_begin_ex(vfi_index_t* idx, const void* q, int q_dtype, int6
     cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
     release_ws(idx, ws);
     return rc;
+  }
+  note_launch(idx, info);
+  std::lock_guard<std::mutex> slock(idx->pool_mu);
+  idx->stats.searches++;
+  idx->stats.queries += nq;
+  const int t = idx->next_ticket;
+  idx->next_ticket = (idx->next_ticket == 0x7FFFFFFF) ? 1 : idx->next_ticket + 1;
+  idx->tickets[t] = ws;
+  ws->ticket = t;
+  *ticket = t;
+  return VFI_OK;
+}
+
+int vfi_index_search_begin_push(vfi_index_t* idx, const void* q, int q_dtype, int64_t nq, int k, float* out_scores, int64_t* out_ids,
+                                vfi_exchange_t* ex, void* stream, int* ticket) {
+  if (!idx || !ticket || !q || !out_scores || !out_ids || !ex || nq <= 0) return fail(VFI_ERR_INVALID, "bad argument to vfi_index_search_begin_push");
+  if (q_dtype != VFI_DTYPE_F32 && q_dtype != VFI_DTYPE_BF16) return fail(VFI_ERR_INVALID, "q_dtype must be VFI_DTYPE_F32 or VFI_DTYPE_BF16");
+  if (k <= 0) return fail(VFI_ERR_INVALID, "k must be positive");
+  if (k > VFI_MAX_K) return fail(VFI_ERR_UNSUPPORTED, "k exceeds VFI_MAX_K (2048)");
+  if (nq > kMaxQueriesPerLaunch) return fail(VFI_ERR_UNSUPPORTED, "vfi_index_search_begin takes at most 1024 queries per batch");
+  if (ex->device != idx->device) return fail(VFI_ERR_INVALID, "the exchange and the index live on different devices");
+  std::shared_lock<std::shared_mutex> lock(idx->rw);
+  DeviceGuard guard(idx->device);
+  if (!guard.ok) return fail(VFI_ERR_CUDA, "cudaSetDevice failed");
+  Workspace* ws = acquire_ws(idx);
+  if (!ws) return VFI_ERR_NOMEM;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the epoch is consumed on every rank whatever path the local search takes: rows that the rescoring kernel does not push
+  // (exact streaming path, k' > 256) are pushed by a kernel of their own right behind the search
+  vfi::PushTarget target{};
+  int rc = exchange_reserve_push(ex, nq, k, &target);
+  if (rc != VFI_OK) {
+    release_ws(idx, ws);
+    return rc;
+  }
+  LaunchInfo info;
+  rc = search_launch(idx, ws, q, q_dtype, static_cast<int>(nq), k, out_scores, out_ids, st, false, &info, &target);
+  if (rc == VFI_OK && !info.pushed)
+    rc = exchange_push_rows(ex, target, out_scores, out_ids, nq, k, ws->needs_check ? ws->flag.as<int>() : nullptr, st);
+  if (rc != VFI_OK) {
+    cudaStreamSynchronize(st);
+    release_ws(idx, ws);
+    return rc;     // NOTE: the epoch stays reserved; the peers' merge of it will time out — a failed collective
   }
   note_launch(idx, info);
   std::lock_guard<std::mutex> slock(idx->pool_mu);

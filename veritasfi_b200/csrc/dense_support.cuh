@@ -11,6 +11,7 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include "peer_exchange.cuh"
 #include "ptx.cuh"
 #include "reduce.cuh"
 #include "select.cuh"
@@ -401,6 +402,7 @@ __global__ void keys_to_scores_kernel(const uint64_t* __restrict__ keys, int64_t
 // completion on a per-warp mbarrier) straight into its own padded shared-memory row: no LSU load instruction, no register
 // staging, no transposition.  One stage per warp; the other resident warps (20 per SM) hide the copy.  The query is
 // widened to fp64 once per CTA.  Floor: the HBM read of the candidate rows, nq * k' * d * sizeof(RowT) bytes.
+// With a PushTarget (sharded search) the kernel is also the sender of the multi-GPU exchange, see the end of the kernel.
 // Round 2 tried two candidates per thread with alternating pieces (the copy of one in flight while the other is summed):
 // 104 us instead of 77 us at 1024 x 128 rows and 49 us instead of 35 us at 256 queries (ncu: 3.4 warps per SM active, stalls on
 // the dependent DFMA chain) — halving the threads doubles every thread's serial fp64 chain, and the kernel is bound by
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(256) rescore_finalize_kernel(
     int keep, const RowT* __restrict__ rows, int64_t row_pitch, int dp, const float* __restrict__ qcanon, int k,
     int64_t id_offset, const float* __restrict__ eps, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
     int* __restrict__ flagged, int* __restrict__ n_flagged, uint32_t* __restrict__ max_err_bits, int* __restrict__ done_ctas,
-    int* __restrict__ host_n_flagged) {
+    int* __restrict__ host_n_flagged, const PushTarget push) {
   static_assert(STAGES <= 4, "barrier slots");
   constexpr int kPitch = PIECE + 16;                 // bytes; conflict-free 128-bit reads of 32 different rows
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -527,6 +529,17 @@ __global__ void __launch_bounds__(256) rescore_finalize_kernel(
     }
   } else if (tid == 0) {
     flagged[atomicAdd(n_flagged, 1)] = q;
+  }
+  // Sharded search: this CTA is the exchange's sender for its query — the ordered row goes straight from shared memory into
+  // every rank's window over NVLink while the other queries are still being rescored, and nothing is waited for; the merge
+  // kernel behind this one publishes the rows (peer_exchange.cuh).  A row whose certificate failed is sent as it is: the
+  // batch's fail bit makes every rank exchange it again after the repair.
+  if (push.world > 0) {
+    push_row_data(push, q, k, [&](int j) -> uint64_t {
+      if (static_cast<uint32_t>(j) >= n) return kKeyNone;
+      const uint64_t key = skeys[j];
+      return make_key(key_score(key), static_cast<uint32_t>(static_cast<int64_t>(key_id(key)) + id_offset));
+    });
   }
   publish_flag_count(n_flagged, done_ctas, host_n_flagged);
 }

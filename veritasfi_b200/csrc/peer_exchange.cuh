@@ -18,6 +18,13 @@
 // Windows are double-buffered by epoch parity: a rank can only start epoch e+2 after its own epoch e+1
 // completed, which needed every peer's epoch e+1 pushes, which those peers issue after finishing their
 // epoch-e reads (stream order) — so overwriting parity e&1 at e+2 never races with a reader.
+// Fused with the compute (round 2): the rescoring kernel K2 (dense_support.cuh: rescore_finalize_kernel) sends — the CTA that has
+// just certified and ordered query q stores that row into every peer's window (push_row_data) while the other queries of the
+// batch are still being rescored, and does not wait for the NVLink round trip; exchange_wait_merge_kernel, next in the stream,
+// first publishes the flags of this rank's rows (with the batch's certificate state as the fail bit), then waits for the peers'
+// and merges.  (First version: K2 published the flags itself behind a system-scope fence — the fence held every K2 CTA for the
+// round trip, +45 us on the kernel for 1024 queries, as much as the separate push phase it replaced.)  The stream order
+// push(e) < merge(e) < push(e+1) on every rank keeps the double-buffer argument above intact.
 // The reference has no counterpart (its workers are replicas, experiments/retriever/step3_mul.py:405-446).
 #pragma once
 #include "select.cuh"
@@ -27,14 +34,24 @@ namespace vfi {
 
 constexpr int kMaxPeers = 16;
 
-struct ExchangeParams {
+// where one rank's rows of one epoch go: a by-value kernel parameter of the pushing kernel (world == 0: no push)
+struct PushTarget {
   uint64_t* win[kMaxPeers];     // window base of every rank as mapped in THIS process (win[rank] is local)
   uint32_t* flags[kMaxPeers];   // flag base of every rank
   int rank, world;
-  int nq, k, k_out;
   int64_t max_nq;               // window geometry: [2][world][max_nq][max_k] keys, flags [2][world][max_nq]
   int max_k;
   uint32_t epoch;               // 1, 2, 3 ... the same sequence on every rank
+};
+
+struct ExchangeParams {
+  uint64_t* win[kMaxPeers];
+  uint32_t* flags[kMaxPeers];
+  int rank, world;
+  int nq, k, k_out;
+  int64_t max_nq;
+  int max_k;
+  uint32_t epoch;
   const float* scores;          // this rank's results [nq][k]
   const int64_t* ids;           // global ids, -1 = padding
   float* out_scores;            // [nq][k_out]
@@ -42,6 +59,9 @@ struct ExchangeParams {
   const int* fail_a;            // device: > 0 when this rank's local results are not final yet (may be null)
   const int* fail_b;
   int* any_fail;                // device: set to 1 when any rank reported fail (may be null)
+  int* fail_acc;                // device, zero between launches: OR of the fail bits seen by this launch's CTAs (may be null)
+  int* done_ctas;               // device, zero between launches: finished CTAs
+  int* host_any_fail;           // mapped host memory: the last CTA stores the OR here — no copy operation in the stream
   unsigned long long timeout_ns;
 };
 
@@ -57,6 +77,42 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+}
+
+// The calling CTA stores row q of this rank (k keys; key_at(j) -> the j-th key with its GLOBAL id, kKeyNone = padding) into
+// slot [parity][rank][q] of every rank's window.  Plain remote stores, nothing waited for: the row is published later by
+// publish_row_flags from a kernel that runs AFTER this one in the stream (its system-scope release store is cumulative over
+// everything that happened before it, and a kernel boundary orders this kernel's stores before it), so a compute kernel can
+// send its results without stalling on the NVLink round trip.
+template <class KeyAt>
+__device__ __forceinline__ void push_row_data(const PushTarget& t, int q, int k, KeyAt key_at) {
+  const uint32_t parity = t.epoch & 1u;
+  const int64_t slot_keys = t.max_nq * t.max_k;
+  const int64_t par_keys = static_cast<int64_t>(t.world) * slot_keys;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const uint64_t key = key_at(j);
+    const int64_t dst = parity * par_keys + t.rank * slot_keys + static_cast<int64_t>(q) * t.max_k + j;
+#pragma unroll 1
+    for (int r = 0; r < t.world; ++r) t.win[(t.rank + r) % t.world][dst] = key;   // start with the local copy, then fan out
+  }
+}
+// flag [parity][rank][q] = epoch << 1 | fail in every rank's flag array; threads 0..world-1 of the CTA store one each
+__device__ __forceinline__ void publish_row_flags(const PushTarget& t, int q, uint32_t fail) {
+  const uint32_t parity = t.epoch & 1u;
+  const int64_t par_flags = static_cast<int64_t>(t.world) * t.max_nq;
+  if (threadIdx.x < static_cast<uint32_t>(t.world)) {
+    const int r = (t.rank + threadIdx.x) % t.world;
+    st_release_sys_u32(t.flags[r] + parity * par_flags + static_cast<int64_t>(t.rank) * t.max_nq + q, (t.epoch << 1) | (fail & 1u));
+  }
+}
+// both in one kernel: the writers order their own stores before the flag.  All threads of the CTA must call (one barrier
+// inside); blockDim.x >= world.
+template <class KeyAt>
+__device__ __forceinline__ void push_row(const PushTarget& t, int q, int k, uint32_t fail, KeyAt key_at) {
+  push_row_data(t, q, k, key_at);
+  __threadfence_system();
+  __syncthreads();
+  publish_row_flags(t, q, fail);
 }
 
 struct WindowSrc {
@@ -76,36 +132,42 @@ struct WindowSrc {
   }
 };
 
-__global__ void __launch_bounds__(256) exchange_merge_kernel(const ExchangeParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  SelectSmem* sm = reinterpret_cast<SelectSmem*>(smem_raw);
-  const uint32_t parity = p.epoch & 1u;
-  const int64_t slot_keys = p.max_nq * p.max_k;                     // keys per (parity, source rank)
-  const int64_t par_keys = static_cast<int64_t>(p.world) * slot_keys;
-  const int64_t par_flags = static_cast<int64_t>(p.world) * p.max_nq;
+__device__ __forceinline__ PushTarget push_target_of(const ExchangeParams& p) {
+  PushTarget t;
+  for (int r = 0; r < kMaxPeers; ++r) { t.win[r] = p.win[r]; t.flags[r] = p.flags[r]; }
+  t.rank = p.rank; t.world = p.world; t.max_nq = p.max_nq; t.max_k = p.max_k; t.epoch = p.epoch;
+  return t;
+}
 
+// push phase: all queries of this CTA first, so the stores of every query are in flight together
+__device__ __forceinline__ void exchange_push_phase(const ExchangeParams& p) {
   const uint32_t my_fail = ((p.fail_a != nullptr && *p.fail_a > 0) || (p.fail_b != nullptr && *p.fail_b > 0)) ? 1u : 0u;
-  const uint32_t stamp = (p.epoch << 1) | my_fail;
-  __shared__ uint32_t s_fail;
-  if (threadIdx.x == 0) s_fail = 0;
-  // ---- push: all queries of this CTA first, so the stores of every query are in flight together
+  const PushTarget t = push_target_of(p);
   for (int q = blockIdx.x; q < p.nq; q += gridDim.x) {
-    for (int j = threadIdx.x; j < p.k; j += blockDim.x) {
+    push_row(t, q, p.k, my_fail, [&](int j) -> uint64_t {
       const int64_t o = static_cast<int64_t>(q) * p.k + j;
       const int64_t id = p.ids[o];
-      const uint64_t key = (id >= 0) ? make_key(p.scores[o], static_cast<uint32_t>(id)) : kKeyNone;
-      const int64_t dst = parity * par_keys + p.rank * slot_keys + static_cast<int64_t>(q) * p.max_k + j;
-#pragma unroll 1
-      for (int r = 0; r < p.world; ++r) p.win[(p.rank + r) % p.world][dst] = key;   // start with the local copy, then fan out
-    }
-    __threadfence_system();   // each writer orders its own stores before the flag
-    __syncthreads();
-    if (threadIdx.x < static_cast<uint32_t>(p.world)) {
-      const int r = (p.rank + threadIdx.x) % p.world;
-      st_release_sys_u32(p.flags[r] + parity * par_flags + static_cast<int64_t>(p.rank) * p.max_nq + q, stamp);
-    }
+      return (id >= 0) ? make_key(p.scores[o], static_cast<uint32_t>(id)) : kKeyNone;
+    });
   }
-  // ---- wait + merge
+}
+
+// wait + merge phase, then the OR of the fail bits for the host
+__device__ __forceinline__ void exchange_publish_phase(const ExchangeParams& p) {
+  const uint32_t my_fail = ((p.fail_a != nullptr && *p.fail_a > 0) || (p.fail_b != nullptr && *p.fail_b > 0)) ? 1u : 0u;
+  const PushTarget t = push_target_of(p);
+  __threadfence_system();
+  for (int q = blockIdx.x; q < p.nq; q += gridDim.x) publish_row_flags(t, q, my_fail);
+}
+
+__device__ __forceinline__ void exchange_wait_merge_phase(const ExchangeParams& p, SelectSmem* sm) {
+  const uint32_t parity = p.epoch & 1u;
+  const int64_t slot_keys = p.max_nq * p.max_k;
+  const int64_t par_keys = static_cast<int64_t>(p.world) * slot_keys;
+  const int64_t par_flags = static_cast<int64_t>(p.world) * p.max_nq;
+  __shared__ uint32_t s_fail;
+  if (threadIdx.x == 0) s_fail = 0;
+  __syncthreads();
   const uint32_t* my_flags = p.flags[p.rank] + parity * par_flags;
   const uint64_t* my_win = p.win[p.rank] + parity * par_keys;
   for (int q = blockIdx.x; q < p.nq; q += gridDim.x) {
@@ -142,7 +204,24 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const ExchangeParam
     }
     __syncthreads();   // sm is reused by the next query
   }
-  if (threadIdx.x == 0 && s_fail != 0 && p.any_fail != nullptr) *p.any_fail = 1;
+  if (threadIdx.x == 0) {
+    if (s_fail != 0) {
+      if (p.any_fail != nullptr) *p.any_fail = 1;
+      if (p.fail_acc != nullptr) atomicOr(p.fail_acc, 1);
+    }
+    if (p.done_ctas != nullptr) {
+      __threadfence();
+      if (atomicAdd(p.done_ctas, 1) == static_cast<int>(gridDim.x) - 1) {
+        __threadfence();
+        *reinterpret_cast<volatile int*>(p.host_any_fail) = *reinterpret_cast<volatile int*>(p.fail_acc);
+        *p.fail_acc = 0;          // ready for the launch that reuses this slot (stream-ordered behind this one)
+        *p.done_ctas = 0;
+        __threadfence_system();
+      }
+    }
+  }
 }
+
+// The three kernels built from these phases (push + wait + merge, push, wait + merge) are defined in api_exchange.cu.
 
 }  // namespace vfi

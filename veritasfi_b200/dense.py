@@ -102,11 +102,13 @@ class DenseIndex:
                                                  N.MEM_DEVICE, _stream_ptr(self.device)))
         return ids, scores
 
-    def search_begin(self, q: torch.Tensor, k: int, out=None) -> "SearchTicket":
+    def search_begin(self, q: torch.Tensor, k: int, out=None, push=None) -> "SearchTicket":
         """Enqueue one batch (B <= 1024) and return at once; `search_finish(ticket)` waits, certifies and hands out
         (ids, scores).  Beginning batch i+1 before finishing batch i keeps the GPU busy while the host looks at the
         certificate flag of batch i (vfi_index_search_begin / vfi_index_search_finish).  out: optional contiguous
-        (ids int64 [B,k], scores float32 [B,k]) tensors to write into."""
+        (ids int64 [B,k], scores float32 [B,k]) tensors to write into.  push: a sharded.PeerExchange — the batch's rescoring
+        kernel then also sends every finished row to the peers' windows (vfi_index_search_begin_push); the caller follows up
+        with push.merge_pushed(...) on the same stream."""
         if not (isinstance(q, torch.Tensor) and q.is_cuda and q.dtype in (torch.float32, torch.bfloat16) and q.dim() == 2
                 and q.shape[1] == self.d and q.shape[0] > 0):
             raise ValueError("search_begin: need a non-empty float32 or bfloat16 [B, d] cuda tensor")
@@ -121,9 +123,14 @@ class DenseIndex:
                     and ids.dtype == torch.int64 and scores.dtype == torch.float32):
                 raise ValueError("search_begin: out must be contiguous (int64 [B,k], float32 [B,k])")
         t = C.c_int(-1)
-        N.check(N.load().vfi_index_search_begin_ex(self._h, C.c_void_p(q.data_ptr()), self._q_dtype(q), B, int(k),
-                                                   C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()),
-                                                   _stream_ptr(self.device), C.byref(t)))
+        if push is not None:
+            N.check(N.load().vfi_index_search_begin_push(self._h, C.c_void_p(q.data_ptr()), self._q_dtype(q), B, int(k),
+                                                         C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()), push._h,
+                                                         _stream_ptr(self.device), C.byref(t)))
+        else:
+            N.check(N.load().vfi_index_search_begin_ex(self._h, C.c_void_p(q.data_ptr()), self._q_dtype(q), B, int(k),
+                                                       C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()),
+                                                       _stream_ptr(self.device), C.byref(t)))
         return SearchTicket(t.value, q, ids, scores)
 
     def search_finish(self, ticket: "SearchTicket"):

@@ -106,6 +106,25 @@ class PeerExchange:
             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         return out_i, out_s
 
+    def merge_pushed(self, B: int, k: int, k_out: int, fail_ptr: int | None = None):
+        """The wait + merge half for rows that a search begun with `DenseIndex.search_begin(..., push=self)` is pushing (or has
+        pushed) on the current stream; fail_ptr: the batch's certificate counter (DenseIndex.ticket_flag_ptr).  Returns (ids [B,k_out], scores [B,k_out], slot); `any_fail(slot)` is valid once an event
+        recorded behind this call has completed.  A collective, like merge."""
+        C, N = self._C, self._N
+        out_s = torch.empty((B, k_out), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((B, k_out), dtype=torch.int64, device=self.device)
+        slot = C.c_int(-1)
+        N.check(N.load().vfi_exchange_merge_pushed(self._h, B, int(k), int(k_out), C.c_void_p(out_s.data_ptr()),
+                                                   C.c_void_p(out_i.data_ptr()), C.c_void_p(fail_ptr) if fail_ptr else None,
+                                                   C.byref(slot),
+                                                   C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return out_i, out_s, slot.value
+
+    def any_fail(self, slot: int) -> bool:
+        v = self._C.c_int(0)
+        self._N.check(self._N.load().vfi_exchange_any_fail(self._h, int(slot), self._C.byref(v)))
+        return v.value != 0
+
     def close(self, barrier: bool = True) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
             torch.cuda.synchronize(self.device)
@@ -117,10 +136,10 @@ class PeerExchange:
 
 class ShardTicket:
     """One sharded batch in flight (ShardedSearcher.search_begin)."""
-    __slots__ = ("local", "out", "slot", "event", "k")
+    __slots__ = ("local", "out", "slot", "event", "k", "pushed")
 
-    def __init__(self, local, out, slot, event, k):
-        self.local, self.out, self.slot, self.event, self.k = local, out, slot, event, k
+    def __init__(self, local, out, slot, event, k, pushed=False):
+        self.local, self.out, self.slot, self.event, self.k, self.pushed = local, out, slot, event, k, pushed
 
 
 class ShardedSearcher:
@@ -143,6 +162,8 @@ class ShardedSearcher:
         self._flags_dev = None
         self._next_slot = 0
         self.re_exchanges = 0
+        import os
+        self.fused_push = os.environ.get("VFI_FUSED_PUSH", "1") != "0"   # 0: the unfused exchange kernel behind the search
 
     def exchange_rows(self, scores: torch.Tensor, ids: torch.Tensor, k_out: int, fail_ptrs=(None, None), any_fail=None):
         """Global top-k_out of every row over the ranks: scores/ids [R,k] per rank (global ids) -> (ids, scores) [R,k_out],
@@ -176,6 +197,16 @@ class ShardedSearcher:
         had to, all ranks exchange that batch once more — they agree on it without a host collective."""
         if self.index is None:
             raise RuntimeError("search_begin needs the DenseIndex behind the local searcher (make_sharded_dense)")
+        if (self.world > 1 and self.exchange is not None and self.fused_push and q.shape[0] <= self.exchange.max_nq
+                and k <= self.exchange.max_k):
+            # compute + collective: the rescoring kernel of the local search sends every finished row to the peers itself (with
+            # that query's certificate verdict), the kernel behind it waits for the peers' rows and merges; the "any rank has
+            # to repair" bit reaches the host through mapped memory — no pack, copy or memset operation in the stream
+            t = self.index.search_begin(q, k, push=self.exchange)
+            oi, os_, slot = self.exchange.merge_pushed(q.shape[0], k, k, self.index.ticket_flag_ptr(t))
+            ev = torch.cuda.Event()
+            ev.record()
+            return ShardTicket(t, (oi, os_), slot, ev, k, True)
         t = self.index.search_begin(q, k)
         if self.world == 1:
             return ShardTicket(t, None, -1, None, k)
@@ -198,7 +229,8 @@ class ShardedSearcher:
         if self.world == 1:
             return ids, scores
         ticket.event.synchronize()
-        if int(self._flags_host[ticket.slot]) != 0:               # the same value on every rank
+        failed = self.exchange.any_fail(ticket.slot) if ticket.pushed else int(self._flags_host[ticket.slot]) != 0
+        if failed:                                                # the same value on every rank
             self.re_exchanges += 1
             return self.exchange_rows(scores, ids, ticket.k)
         return ticket.out
