@@ -423,40 +423,42 @@ def run_dense(args, name, w, ctx, config, steps, warmup, result_out):
         for _ in range(k_steps):   # the reference-facing host call of the C ABI: H2D, search, D2H inside
             index.search_host_into(q_pin[0].data_ptr(), w["b"], w["k"], out_s_pin[0].data_ptr(), out_i_pin[0].data_ptr(), e2e_stream)
 
-    copy_stream = torch.cuda.Stream(device=ctx.dev)
+    h2d_stream = torch.cuda.Stream(device=ctx.dev)
+    d2h_stream = torch.cuda.Stream(device=ctx.dev)
     h2d_done = [torch.cuda.Event() for _ in range(n_buf)]
-    res_ready = [torch.cuda.Event() for _ in range(n_buf)]
 
     def run_e2e_pipelined(k_steps):
         """Host buffers through the sharded searcher: per batch a pinned H2D copy of its queries, the search (+ exchange),
-        a D2H read of its ids and scores; two batches in flight.  The copies run on a second stream (H2D of batch i+1 and
-        D2H of batch i-1 overlap the kernels of batch i) and every one of them lies inside the timed region."""
+        a D2H read of its ids and scores; two batches in flight.  The copies run on streams of their own (H2D of batch i+1 and
+        D2H of batch i-1 overlap the kernels of batch i) and every one of them lies inside the timed region.  search_finish
+        returns when the batch is complete on the device, so its D2H copy needs no event from the main stream — an event
+        recorded there would sit behind the NEXT batch's kernels and hold the copy (and the H2D queued behind it) back."""
         main = torch.cuda.current_stream(ctx.dev)
-        copy_stream.wait_stream(main)
+        h2d_stream.wait_stream(main)
+        d2h_stream.wait_stream(main)
 
         def drain(prev):
             ids, scores = searcher.search_finish(prev[0])
-            res_ready[prev[1]].record(main)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(res_ready[prev[1]])
+            with torch.cuda.stream(d2h_stream):
                 out_i_pin[prev[1]].copy_(ids, non_blocking=True)
                 out_s_pin[prev[1]].copy_(scores, non_blocking=True)
-                ids.record_stream(copy_stream)
-                scores.record_stream(copy_stream)
+                ids.record_stream(d2h_stream)
+                scores.record_stream(d2h_stream)
 
         prev = None
         for i in range(k_steps):
             s = i % n_buf
-            with torch.cuda.stream(copy_stream):
+            with torch.cuda.stream(h2d_stream):
                 q_stage[s].copy_(q_pin[s], non_blocking=True)
-                h2d_done[s].record(copy_stream)
+                h2d_done[s].record(h2d_stream)
             main.wait_event(h2d_done[s])
             t = searcher.search_begin(q_stage[s], w["k"])
             if prev is not None:
                 drain(prev)
             prev = (t, s)
         drain(prev)
-        main.wait_stream(copy_stream)
+        main.wait_stream(h2d_stream)
+        main.wait_stream(d2h_stream)
         torch.cuda.synchronize()
 
     run_e2e = run_e2e_host_call if ctx.world == 1 else run_e2e_pipelined

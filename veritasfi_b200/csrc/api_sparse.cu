@@ -1,6 +1,8 @@
 // api_sparse.cu — the sparse and fusion half of include/vfi.h: vfi_bm25_* (bm25s.BM25.retrieve), vfi_merge_topk,
 // vfi_fuse_rrf / vfi_fuse_union / vfi_fuse_hybrid.  Host orchestration of the kernels in sparse_fuse.cuh (K3, K4, K5),
 // reduce.cuh (K1c, K2b) and radix_sort.cuh.
+#include <cstdlib>
+
 #include "api_common.h"
 #include "radix_sort.cuh"
 #include "reduce.cuh"
@@ -346,6 +348,9 @@ int vfi_bm25_search(vfi_bm25_t* b, const int32_t* q_tokens, const int64_t* q_ind
   auto body = [&]() -> int {
     const int64_t n_tok = q_indptr[nq];
     const int keep = static_cast<int>(round_up(k, 32));
+    // Key buffer of k' + 256 keys rounded to a power of two (512 keys for a depth-200 list): with the 32 KB range
+    // accumulator that is 42 KB per CTA, five CTAs (40 warps) per SM.  Round 2, C4 shard: 2.05 ms with a 2048-key buffer
+    // compacted by a bitonic sort and four CTAs per SM, 1.78 ms with the radix-walk compaction, 1.69 ms with five CTAs.
     int cap = 1;
     while (cap < keep + vfi::kBmScan) cap <<= 1;
     const size_t smem = ((sizeof(vfi::Bm25Smem) + 15) & ~size_t(15)) + static_cast<size_t>(cap) * 8;
@@ -445,7 +450,7 @@ int vfi_bm25_search(vfi_bm25_t* b, const int32_t* q_tokens, const int64_t* q_ind
 // all scores of one query into `dump` (device fp32 [n_docs]); enqueued on st, tokens staged in w
 static int bm25_dump_scores(vfi_bm25* b, BmScratch* w, const int32_t* q_tokens, int64_t n_tokens, float* dump, cudaStream_t st) {
   const int64_t qptr[2] = {0, n_tokens};
-  const int cap = 2048;
+  const int cap = 32;       // the key buffer is not used when every score is written out
   const size_t smem = ((sizeof(vfi::Bm25Smem) + 15) & ~size_t(15)) + static_cast<size_t>(cap) * 8;
   int occ = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vfi::bm25_kernel, vfi::kBmThreads, smem) != cudaSuccess) {

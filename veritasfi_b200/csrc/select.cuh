@@ -8,13 +8,18 @@ namespace vfi {
 
 constexpr uint32_t kSortCap = 4096;  // keys sortable in shared memory by one CTA (32 KB)
 
+// scratch of the block-wide MSD radix walk (block_kth_key)
+struct RadixScratch {
+  uint32_t hist[256];
+  uint32_t digit, before, cnt, seen;
+};
+
 template <uint32_t CAP>
 struct SelectSmemT {
   static constexpr uint32_t kCap = CAP;   // keys sortable in shared memory (multiple of 256)
   uint64_t keys[CAP];
-  uint32_t hist[256];
+  RadixScratch rs;
   uint32_t ctr;
-  uint32_t digit, before, cnt, seen;
 };
 using SelectSmem = SelectSmemT<kSortCap>;
 
@@ -150,32 +155,31 @@ __device__ inline bool merge_sorted_rows(const uint64_t* keys, int rows, int k, 
 // of one query share their leading bytes, so plain atomics would serialise on one bin).  Three barriers per pass and at
 // most 8 passes (typically 3-4: the walk stops as soon as a bin holds exactly the keys still wanted), against the 55
 // barrier-separated stages of a 1024-key bitonic sort.  blockDim.x must be a multiple of 32, >= 64.  All threads must call.
-template <class SM>
-__device__ __forceinline__ uint64_t block_kth_key_smem(SM* sm, uint32_t n, uint32_t k) {
+__device__ __forceinline__ uint64_t block_kth_key(const uint64_t* keys, uint32_t n, uint32_t k, RadixScratch* rs) {
   const uint32_t tid = threadIdx.x, lane = tid & 31;
   if (n < k) return 0ull;
   uint64_t prefix = 0;
   uint32_t remaining = k;
   for (int shift = 56; shift >= 0 && n > k; shift -= 8) {
-    for (uint32_t i = tid; i < 256; i += blockDim.x) sm->hist[i] = 0;
+    for (uint32_t i = tid; i < 256; i += blockDim.x) rs->hist[i] = 0;
     __syncthreads();
     const uint64_t himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
     for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {     // warp-uniform trip count: every lane takes part in the match
       const uint32_t i = i0 + tid;
       uint32_t digit = 0xFFFFFFFFu;
       if (i < n) {
-        const uint64_t key = sm->keys[i];
+        const uint64_t key = keys[i];
         if ((key & himask) == prefix) digit = static_cast<uint32_t>(key >> shift) & 0xFFu;
       }
       const uint32_t peers = __match_any_sync(0xFFFFFFFFu, digit);
-      if (digit != 0xFFFFFFFFu && lane == static_cast<uint32_t>(__ffs(peers) - 1)) atomicAdd(&sm->hist[digit], __popc(peers));
+      if (digit != 0xFFFFFFFFu && lane == static_cast<uint32_t>(__ffs(peers) - 1)) atomicAdd(&rs->hist[digit], __popc(peers));
     }
     __syncthreads();
-    if (tid < 32) hist_find_bin(sm->hist, remaining, tid, &sm->digit, &sm->before, &sm->cnt, &sm->seen);
+    if (tid < 32) hist_find_bin(rs->hist, remaining, tid, &rs->digit, &rs->before, &rs->cnt, &rs->seen);
     __syncthreads();
-    prefix |= static_cast<uint64_t>(sm->digit) << shift;
-    remaining -= sm->before;
-    const bool stop = (sm->cnt == remaining) || shift == 0;
+    prefix |= static_cast<uint64_t>(rs->digit) << shift;
+    remaining -= rs->before;
+    const bool stop = (rs->cnt == remaining) || shift == 0;
     __syncthreads();
     if (stop) break;
   }
@@ -185,7 +189,7 @@ __device__ __forceinline__ uint64_t block_kth_key_smem(SM* sm, uint32_t n, uint3
   __syncthreads();
   unsigned long long mn = ~0ull;
   for (uint32_t i = tid; i < n; i += blockDim.x) {
-    const uint64_t key = sm->keys[i];
+    const uint64_t key = keys[i];
     if (key >= prefix && key < mn) mn = key;
   }
 #pragma unroll
@@ -195,7 +199,13 @@ __device__ __forceinline__ uint64_t block_kth_key_smem(SM* sm, uint32_t n, uint3
   }
   if (lane == 0 && mn != ~0ull) atomicMin(&s_min, mn);
   __syncthreads();
-  return s_min;
+  const uint64_t out = s_min;
+  __syncthreads();     // s_min may be re-initialised by the next call
+  return out;
+}
+template <class SM>
+__device__ __forceinline__ uint64_t block_kth_key_smem(SM* sm, uint32_t n, uint32_t k) {
+  return block_kth_key(sm->keys, n, k, &sm->rs);
 }
 
 // Src: struct with   template<class F> __device__ void for_each(F f) const
@@ -245,23 +255,23 @@ __device__ uint32_t block_topk(const Src& src, uint32_t total, uint32_t k, SM* s
     uint64_t prefix = 0;
     uint32_t remaining = k;
     for (int shift = 56; shift >= 0; shift -= 8) {
-      if (tid < 256) sm->hist[tid] = 0;
+      if (tid < 256) sm->rs.hist[tid] = 0;
       __syncthreads();
       const uint64_t himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
       src.for_each([&](uint64_t key) {
-        if ((key & himask) == prefix && key != 0ull) atomicAdd(&sm->hist[(key >> shift) & 0xFF], 1u);
+        if ((key & himask) == prefix && key != 0ull) atomicAdd(&sm->rs.hist[(key >> shift) & 0xFF], 1u);
       });
       __syncthreads();
-      if (tid < 32) hist_find_bin(sm->hist, remaining, tid, &sm->digit, &sm->before, &sm->cnt, &sm->seen);
+      if (tid < 32) hist_find_bin(sm->rs.hist, remaining, tid, &sm->rs.digit, &sm->rs.before, &sm->rs.cnt, &sm->rs.seen);
       __syncthreads();
-      if (sm->seen <= remaining) {   // fewer real keys than asked for (padding in the source): keep them all
+      if (sm->rs.seen <= remaining) {   // fewer real keys than asked for (padding in the source): keep them all
         __syncthreads();
         prefix = 0;
         break;
       }
-      prefix |= static_cast<uint64_t>(sm->digit) << shift;
-      remaining -= sm->before;
-      const bool stop = (sm->cnt == remaining) || shift == 0;
+      prefix |= static_cast<uint64_t>(sm->rs.digit) << shift;
+      remaining -= sm->rs.before;
+      const bool stop = (sm->rs.cnt == remaining) || shift == 0;
       __syncthreads();
       if (stop) break;
     }
