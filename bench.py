@@ -49,6 +49,7 @@ WORKLOADS = {
     "c4small": dict(kind="hybrid", n=60_000, n_ts=12_000, d=256, b=64, k=20, depth=50, vocab=8192, mean_len=40, desc="smoke-size hybrid"),
     "c3s8": dict(kind="dense", n=1_250_000, d=1024, b=1024, k=100, desc="one 1/8 row shard of C3 (1.25Mx1024 bf16), 1024-query batch, top-100"),
     "c3q": dict(kind="dense", n=2_500_000, d=1024, b=1024, k=100, desc="a quarter of C3 (2.5Mx1024 bf16; on two GPUs each shard is the 1.25M rows of an 8-GPU C3 run), 1024-query batch, top-100"),
+    "d200": dict(kind="dense", n=625_000, d=1024, b=1024, k=200, desc="the chunk path of one C4 shard alone (625kx1024 bf16, 1024 queries, depth 200: k' = 256)"),
     "b16": dict(kind="dense", n=1_000_000, d=1024, b=16, k=100, desc="1Mx1024 bf16 corpus, 16-query batch, top-100 (serving batch)"),
     "b64": dict(kind="dense", n=1_000_000, d=1024, b=64, k=100, desc="1Mx1024 bf16 corpus, 64-query batch, top-100 (serving batch)"),
     "b128": dict(kind="dense", n=1_000_000, d=1024, b=128, k=100, desc="1Mx1024 bf16 corpus, 128-query batch, top-100 (serving batch)"),
@@ -566,7 +567,9 @@ def run_latency(args, name, w, ctx, config, steps, warmup, result_out):
     def calls(k_steps):
         for _ in range(k_steps):
             t0 = time.perf_counter()
-            searcher.search(q_dev, w["k"])
+            # one batch in flight: the local search with the exchange enqueued right behind it (the rescoring kernel sends
+            # its row to the peers itself), then one wait for both — no host round trip between search and exchange
+            searcher.search_finish(searcher.search_begin(q_dev, w["k"]))
             torch.cuda.synchronize()
             lat.append((time.perf_counter() - t0) * 1e3)
 

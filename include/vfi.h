@@ -142,6 +142,7 @@ enum {
                                 128-query tiles gets a padding tile): 0 auto = on, 1 off (single-CTA kernel), 2 on */
   VFI_OPT_SMALL_BATCH = 10,  /* 0 auto: batches of 9..64 queries run the swapped-operand tcgen05 kernel (corpus rows on the M side,
                                 the query block resident in shared memory: the corpus stream is the only traffic); 1 off */
+  VFI_OPT_TAIL_PIECE = 11,   /* bytes per lane and step of the rescoring kernel's row gather: 0 auto, 128, 256 */
   VFI_OPT_TAU_M = 9          /* admission hint = the m-th best score of a row sample: 0 auto (8 for large shards; 16 or 32 with a
                                 denser sample when k'/N is large and passing rows would swamp the epilogue), or 8 / 16 / 32 */
 };

@@ -13,6 +13,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 STORE_BF16, STORE_F32 = 0, 1
 DTYPE_F32, DTYPE_BF16 = 0, 1
 OPT_OVERFETCH, OPT_FORCE_PATH, OPT_PROFILE, OPT_TAU_HINT, OPT_NUM_CTAS, OPT_CTA_PAIR, OPT_TAU_M, OPT_SMALL_BATCH = 1, 2, 3, 4, 5, 7, 9, 10
+OPT_TAIL_PIECE = 11
 PATH_AUTO, PATH_EXACT, PATH_FUSED, PATH_GEMV = 0, 1, 2, 3
 PATH_EXHAUSTIVE = PATH_EXACT   # the old name: every row scored canonically
 MAX_K = 2048

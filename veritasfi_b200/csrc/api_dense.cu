@@ -199,7 +199,7 @@ struct vfi_index {
   DevBuf stage;            // add()/read_rows staging (writer lock / own lock)
   std::mutex stage_mu;
   // options (written under the writer lock)
-  int64_t opt_overfetch = 0, opt_force_path = 0, opt_profile = 0, opt_tau_hint = 1, opt_num_ctas = 0, opt_cta_pair = 0, opt_tau_m = 0, opt_small = 0;
+  int64_t opt_overfetch = 0, opt_force_path = 0, opt_profile = 0, opt_tau_hint = 1, opt_num_ctas = 0, opt_cta_pair = 0, opt_tau_m = 0, opt_small = 0, opt_tail_piece = 0;
   std::shared_mutex rw;    // searches share it, add/reserve/options own it
   std::mutex pool_mu;      // workspace pool, tickets, stats
   std::vector<std::unique_ptr<Workspace>> pool;
@@ -286,6 +286,10 @@ int vfi_index_create(int d, int store_dtype, int device, vfi_index_t** out) {
                          static_cast<int>(vfi::rescore_bulk_smem<256>(vfi::kRfMaxDp, 256, 1)));
     cudaFuncSetAttribute(vfi::rescore_finalize_kernel<float, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          static_cast<int>(vfi::rescore_bulk_smem<256>(vfi::kRfMaxDp, 256, 1)));
+    cudaFuncSetAttribute(vfi::rescore_finalize_kernel<uint16_t, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(vfi::rescore_bulk_smem<128>(vfi::kRfMaxDp, 256, 1)));
+    cudaFuncSetAttribute(vfi::rescore_finalize_kernel<float, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(vfi::rescore_bulk_smem<128>(vfi::kRfMaxDp, 256, 1)));
   });
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return bail(fail(VFI_ERR_CUDA, std::string("kernel attribute setup: ") + cudaGetErrorString(e)));
@@ -445,6 +449,10 @@ int vfi_index_set_option(vfi_index_t* idx, int opt, int64_t value) {
     case VFI_OPT_SMALL_BATCH:
       if (value < 0 || value > 1) return fail(VFI_ERR_INVALID, "VFI_OPT_SMALL_BATCH: 0 auto (swapped-operand kernel for 9..64 queries), 1 off");
       idx->opt_small = value;
+      break;
+    case VFI_OPT_TAIL_PIECE:
+      if (value != 0 && value != 128 && value != 256) return fail(VFI_ERR_INVALID, "VFI_OPT_TAIL_PIECE: 0 auto, 128 or 256");
+      idx->opt_tail_piece = value;
       break;
     case VFI_OPT_CTA_PAIR:
       if (value < 0 || value > 2) return fail(VFI_ERR_INVALID, "VFI_OPT_CTA_PAIR: 0 auto, 1 off, 2 on");
@@ -869,17 +877,31 @@ int search_launch(vfi_index* idx, Workspace* ws, const void* q_dev, int q_dtype,
       info->pushed = true;
     }
     const int threads = static_cast<int>(round_up(keep, 32));
-    const size_t smem = vfi::rescore_bulk_smem<256>(static_cast<int>(idx->dp), threads, 1);
-    if (idx->store == VFI_STORE_F32)
-      vfi::rescore_finalize_kernel<float, 256, 1><<<nq, threads, smem, st>>>(
-          ws->keys.as<uint64_t>(), ws->keys_n.as<uint32_t>(), ws->bound.as<float>(), keep, idx->master, static_cast<int64_t>(idx->dp),
-          static_cast<int>(idx->dp), ws->qcanon.as<float>(), k, idx->id_offset, ws->eps.as<float>(), out_scores, out_ids, d_flag + 1,
-          d_flag, idx->d_max_err, d_done, ws->h_flag_dev, pt);
-    else
-      vfi::rescore_finalize_kernel<uint16_t, 256, 1><<<nq, threads, smem, st>>>(
-          ws->keys.as<uint64_t>(), ws->keys_n.as<uint32_t>(), ws->bound.as<float>(), keep, idx->g, idx->kp, static_cast<int>(idx->dp),
-          ws->qcanon.as<float>(), k, idx->id_offset, ws->eps.as<float>(), out_scores, out_ids, d_flag + 1, d_flag, idx->d_max_err,
-          d_done, ws->h_flag_dev, pt);
+    // Bytes per lane and step of the row gather.  256-byte pieces reach the higher gather bandwidth, 128-byte pieces halve
+    // the shared memory per CTA: measured (round 2, A/B in one process), 128 wins when the queries do not fit one wave
+    // of 256-byte CTAs (1024 queries: k' = 256 tail 0.229 -> 0.218 ms, k' = 128 tail 0.142 -> 0.139 ms) and loses when the
+    // grid is a fraction of a wave and every CTA is latency-bound (256 queries, k' = 128: 0.071 -> 0.091 ms).
+    int piece = static_cast<int>(idx->opt_tail_piece);
+    if (piece == 0) {
+      const size_t smem256 = vfi::rescore_bulk_smem<256>(static_cast<int>(idx->dp), threads, 1);
+      const int occ256 = static_cast<int>(std::max<size_t>(1, std::min<size_t>(228 * 1024 / (smem256 + 1024), static_cast<size_t>(2048 / threads))));
+      piece = (nq > idx->num_sms * occ256) ? 128 : 256;
+    }
+    const size_t smem = piece == 128 ? vfi::rescore_bulk_smem<128>(static_cast<int>(idx->dp), threads, 1)
+                                     : vfi::rescore_bulk_smem<256>(static_cast<int>(idx->dp), threads, 1);
+#define VFI_RESCORE(RowT, PIECE, ROWS, PITCH)                                                                                 \
+    vfi::rescore_finalize_kernel<RowT, PIECE, 1><<<nq, threads, smem, st>>>(                                                   \
+        ws->keys.as<uint64_t>(), ws->keys_n.as<uint32_t>(), ws->bound.as<float>(), keep, ROWS, PITCH,                          \
+        static_cast<int>(idx->dp), ws->qcanon.as<float>(), k, idx->id_offset, ws->eps.as<float>(), out_scores, out_ids,        \
+        d_flag + 1, d_flag, idx->d_max_err, d_done, ws->h_flag_dev, pt)
+    if (idx->store == VFI_STORE_F32) {
+      if (piece == 128) VFI_RESCORE(float, 128, idx->master, static_cast<int64_t>(idx->dp));
+      else VFI_RESCORE(float, 256, idx->master, static_cast<int64_t>(idx->dp));
+    } else {
+      if (piece == 128) VFI_RESCORE(uint16_t, 128, idx->g, idx->kp);
+      else VFI_RESCORE(uint16_t, 256, idx->g, idx->kp);
+    }
+#undef VFI_RESCORE
     LAUNCHED();
     VFI_CUDA(cudaGetLastError());
   } else {
