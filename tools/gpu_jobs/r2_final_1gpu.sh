@@ -23,6 +23,12 @@ python bench.py --workload $wl --no-cpu-baseline --no-small 2>gpurun_out/e.err >
 done
 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2_bench_reference_arm.json 2>gpurun_out/e.err || tail -5 gpurun_out/e.err
 VFI_TRACE_HOST=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>gpurun_out/r2_trace_host.err >/dev/null; grep "vfi trace" gpurun_out/r2_trace_host.err | tail -12
+# per-operation device times of a batch (one event behind every stream operation)
+: > gpurun_out/r2_step_trace.txt
+for wl in c3s8 c2 c3; do
+  VFI_TRACE_STEPS=1 python tools/trace_steps.py --workload $wl --profile 0 --steps 8 2>&1 | grep -A12 "^--- $wl" | tail -6 | sed "s/^/[$wl] /" >> gpurun_out/r2_step_trace.txt
+done
+cat gpurun_out/r2_step_trace.txt
 # ---- ncu: launch lists (shares of a step) and full captures of the kernels profiles/ quotes
 for wl in c3 c2 c4s8; do
   python tools/prof_step.py --workload $wl --steps 2 --warmup 2 > gpurun_out/plain_$wl.log 2>&1 &&

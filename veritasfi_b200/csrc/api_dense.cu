@@ -878,14 +878,15 @@ int search_launch(vfi_index* idx, Workspace* ws, const void* q_dev, int q_dtype,
     }
     const int threads = static_cast<int>(round_up(keep, 32));
     // Bytes per lane and step of the row gather.  256-byte pieces reach the higher gather bandwidth, 128-byte pieces halve
-    // the shared memory per CTA: measured (round 2, A/B in one process), 128 wins when the queries do not fit one wave
-    // of 256-byte CTAs (1024 queries: k' = 256 tail 0.229 -> 0.218 ms, k' = 128 tail 0.142 -> 0.139 ms) and loses when the
-    // grid is a fraction of a wave and every CTA is latency-bound (256 queries, k' = 128: 0.071 -> 0.091 ms).
+    // the shared memory per CTA (four CTAs of 256 threads per SM instead of two).  Measured (round 2, A/B in one process,
+    // profiles/r2_exp_rescore_piece.jsonl): for depth-200 lists (k' = 256) and 1024 queries the tail is 5-8 % faster with
+    // 128-byte pieces; at k' = 128 the two are within 1-5 % of each other live (and the 256-byte form is the faster one when
+    // the kernel is timed alone under ncu); a grid that is a fraction of a wave (256 queries) is 25 % slower with 128.
     int piece = static_cast<int>(idx->opt_tail_piece);
     if (piece == 0) {
       const size_t smem256 = vfi::rescore_bulk_smem<256>(static_cast<int>(idx->dp), threads, 1);
       const int occ256 = static_cast<int>(std::max<size_t>(1, std::min<size_t>(228 * 1024 / (smem256 + 1024), static_cast<size_t>(2048 / threads))));
-      piece = (nq > idx->num_sms * occ256) ? 128 : 256;
+      piece = (threads > 128 && nq > idx->num_sms * occ256) ? 128 : 256;
     }
     const size_t smem = piece == 128 ? vfi::rescore_bulk_smem<128>(static_cast<int>(idx->dp), threads, 1)
                                      : vfi::rescore_bulk_smem<256>(static_cast<int>(idx->dp), threads, 1);
