@@ -944,8 +944,12 @@ void note_launch(vfi_index* idx, const LaunchInfo& info) {
 
 // Wait for the batch in `ws`, read its certificate flag and repair what failed: a batch pruned too hard by the admission
 // hint is redone without it, queries whose candidates tie across the cut are re-run by the exact streaming pass.
-int search_finish(vfi_index* idx, Workspace* ws) {
-  VFI_CUDA(cudaEventSynchronize(ws->done));
+// whole_stream: wait for everything enqueued on the batch's stream (a host-buffer call has its result copies queued behind the
+// batch: one host wake-up instead of two); *repaired: the results were rewritten after the first wait.
+int search_finish(vfi_index* idx, Workspace* ws, bool whole_stream = false, bool* repaired = nullptr) {
+  if (repaired) *repaired = false;
+  if (whole_stream) VFI_CUDA(cudaStreamSynchronize(ws->st));
+  else VFI_CUDA(cudaEventSynchronize(ws->done));
   if (g_trace_steps && ws->needs_check && ws->tev[8]) {
     static const char* names[9] = {"start", "prep", "-", "sample", "tau", "K1", "cand_reduce", "rescore", "-"};
     float t0 = 0.f;
@@ -984,14 +988,18 @@ int search_finish(vfi_index* idx, Workspace* ws) {
       idx->stats.hint_retries++;
     }
     LaunchInfo info;
+    if (repaired) *repaired = true;
     VFI_TRY(search_launch(idx, ws, ws->q, ws->q_dtype, ws->nq, ws->k, ws->o_scores, ws->o_ids, ws->st, true, &info));
-    return search_finish(idx, ws);
+    const int rc = search_finish(idx, ws);
+    if (repaired) *repaired = true;
+    return rc;
   }
   {
     std::lock_guard<std::mutex> lock(idx->pool_mu);
     idx->stats.retried_queries += n_flagged;
   }
   // the prepared queries of this batch are still in its workspace
+  if (repaired) *repaired = true;
   VFI_TRY(exact_pass(idx, ws, ws->flag.as<int>() + 1, n_flagged, ws->k, ws->o_scores, ws->o_ids, ws->st, false));
   VFI_CUDA(cudaStreamSynchronize(ws->st));
   return VFI_OK;
@@ -1052,12 +1060,25 @@ int vfi_index_search_ex(vfi_index_t* idx, const void* q_any, int q_dtype, int64_
       VFI_TRY(search_launch(idx, ws, qd, q_dtype, nb, k, os, oi, st, false, &info));
       note_launch(idx, info);
       if (trace) t_launch = now();
-      VFI_TRY(search_finish(idx, ws));
-      if (trace) t_finish = now();
       if (mem == VFI_MEM_HOST) {
-        VFI_CUDA(cudaMemcpyAsync(out_scores + q0 * k, os, static_cast<size_t>(nb) * k * 4, cudaMemcpyDeviceToHost, st));
-        VFI_CUDA(cudaMemcpyAsync(out_ids + q0 * k, oi, static_cast<size_t>(nb) * k * 8, cudaMemcpyDeviceToHost, st));
-        VFI_CUDA(cudaStreamSynchronize(st));
+        // The result copies are queued right behind the batch and the host waits once for all of it; the certificate almost
+        // never fails, and when it does the repaired results are copied again.
+        auto copy_out = [&]() -> int {
+          VFI_CUDA(cudaMemcpyAsync(out_scores + q0 * k, os, static_cast<size_t>(nb) * k * 4, cudaMemcpyDeviceToHost, st));
+          VFI_CUDA(cudaMemcpyAsync(out_ids + q0 * k, oi, static_cast<size_t>(nb) * k * 8, cudaMemcpyDeviceToHost, st));
+          return VFI_OK;
+        };
+        VFI_TRY(copy_out());
+        bool repaired = false;
+        VFI_TRY(search_finish(idx, ws, true, &repaired));
+        if (trace) t_finish = now();
+        if (repaired) {
+          VFI_TRY(copy_out());
+          VFI_CUDA(cudaStreamSynchronize(st));
+        }
+      } else {
+        VFI_TRY(search_finish(idx, ws));
+        if (trace) t_finish = now();
       }
       return VFI_OK;
     };
