@@ -133,6 +133,108 @@ def _gloo_worker(rank, world, port, n, d, k, out_path):
     dist.destroy_process_group()
 
 
+def _gloo_fused_worker(rank, world, port, out_path):
+    """The control flow of the pipelined sharded search whose local search pushes its rows (ShardedSearcher.search_begin /
+    search_finish on the fused route) with CPU stand-ins for the index and the peer exchange: tickets, the any-rank-failed bit,
+    the repeat exchange after a repair on ONE rank."""
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from oracle import flat_ip as fi, sharded as so
+    from veritasfi_b200 import sharded as sh
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, d, k = 257, 16, 7
+    rng = np.random.default_rng(5)
+    xb = fi.normalize_l2(rng.standard_normal((n, d)).astype(np.float32))
+    xq = fi.normalize_l2(rng.standard_normal((6, d)).astype(np.float32))
+    lo, hi = sh.shard_bounds(n, world, rank)
+
+    class Ticket:
+        def __init__(self, ids, scores, broken):
+            self.ids, self.scores, self.broken = ids, scores, broken
+
+    class FakeIndex:                      # DenseIndex's pipelined surface; batch 1 of rank 0 "fails its certificate"
+        def __init__(self):
+            self.begun = 0
+
+        def search_begin(self, q, kk, out=None, push=None):
+            D, I = fi.search_exhaustive(q.numpy(), xb[lo:hi], kk, id_base=lo)
+            broken = rank == 0 and self.begun == 1
+            self.begun += 1
+            if broken:                    # rows that are not final yet: what finish() will repair
+                D = D.copy()
+                D[:, 0] = -1.0
+            t = Ticket(torch.from_numpy(I), torch.from_numpy(D), broken)
+            if push is not None:
+                push.pushed_rows = (t.scores.clone(), t.ids.clone(), broken)
+            return t
+
+        def search_finish(self, t):
+            if t.broken:                  # the repair
+                D, I = fi.search_exhaustive(xq, xb[lo:hi], k, id_base=lo)
+                t.ids, t.scores = torch.from_numpy(I), torch.from_numpy(D)
+            return t.ids, t.scores
+
+        def ticket_flag_ptr(self, t):
+            return 0
+
+    class FakeExchange:                   # PeerExchange's surface over gloo collectives
+        max_nq, max_k = 64, 64
+
+        def __init__(self):
+            self.flags, self.pushed_rows = [], None
+
+        def _gather(self, scores, ids, fail):
+            gs = [torch.empty_like(scores) for _ in range(world)]
+            gi = [torch.empty_like(ids) for _ in range(world)]
+            dist.all_gather(gs, scores.contiguous())
+            dist.all_gather(gi, ids.contiguous())
+            f = torch.tensor([1 if fail else 0])
+            dist.all_reduce(f, op=dist.ReduceOp.MAX)
+            return torch.stack(gs), torch.stack(gi), bool(f.item())
+
+        def merge_pushed(self, B, kk, k_out, fail_ptr=None):
+            scores, ids, broken = self.pushed_rows
+            gs, gi, any_fail = self._gather(scores, ids, broken)
+            oi, os_ = so.merge(gs.numpy(), gi.numpy(), k_out)
+            self.flags.append(any_fail)
+            return torch.from_numpy(oi), torch.from_numpy(os_), len(self.flags) - 1
+
+        def any_fail(self, slot):
+            return self.flags[slot]
+
+        def merge(self, scores, ids, k_out, fail_ptrs=(None, None), any_fail=None, out=None):
+            gs, gi, _ = self._gather(scores, ids, False)
+            oi, os_ = so.merge(gs.numpy(), gi.numpy(), k_out)
+            return torch.from_numpy(oi), torch.from_numpy(os_)
+
+    s = sh.ShardedSearcher(None, None, exchange=FakeExchange(), index=FakeIndex())
+    q = torch.from_numpy(xq)
+    D0, I0 = fi.search_exhaustive(xq, xb, k)
+    tickets = [s.search_begin(q, k) for _ in range(3)]
+    ok = all(t.pushed for t in tickets)
+    for t in tickets:
+        ids, scores = s.search_finish(t)
+        ok &= bool((ids.numpy() == I0).all() and (scores.numpy() == D0).all())
+    ok &= s.re_exchanges == 1             # on BOTH ranks, though only rank 0 repaired
+    with open(f"{out_path}.{rank}", "w") as f:
+        f.write("ok" if ok else "mismatch")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_fused_push_control_flow_and_repeat_exchange(tmp_path):
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "res")
+    mp.spawn(_gloo_fused_worker, args=(2, port, out), nprocs=2, join=True)
+    assert open(out + ".0").read() == "ok" and open(out + ".1").read() == "ok"
+
+
 def test_world_size_2_gloo_allgather_merge_equals_unsharded(tmp_path):
     import torch.multiprocessing as mp
     s = socket.socket()

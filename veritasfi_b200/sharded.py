@@ -204,8 +204,10 @@ class ShardedSearcher:
             # to repair" bit reaches the host through mapped memory — no pack, copy or memset operation in the stream
             t = self.index.search_begin(q, k, push=self.exchange)
             oi, os_, slot = self.exchange.merge_pushed(q.shape[0], k, k, self.index.ticket_flag_ptr(t))
-            ev = torch.cuda.Event()
-            ev.record()
+            ev = None
+            if q.is_cuda:            # (a CPU stand-in for index and exchange exercises this control flow under gloo)
+                ev = torch.cuda.Event()
+                ev.record()
             return ShardTicket(t, (oi, os_), slot, ev, k, True)
         t = self.index.search_begin(q, k)
         if self.world == 1:
@@ -228,7 +230,8 @@ class ShardedSearcher:
         ids, scores = self.index.search_finish(ticket.local)     # waits for the local batch, repairs flagged queries
         if self.world == 1:
             return ids, scores
-        ticket.event.synchronize()
+        if ticket.event is not None:
+            ticket.event.synchronize()
         failed = self.exchange.any_fail(ticket.slot) if ticket.pushed else int(self._flags_host[ticket.slot]) != 0
         if failed:                                                # the same value on every rank
             self.re_exchanges += 1
