@@ -104,6 +104,10 @@ class ClockSampler:
             time.sleep(0.08)
             n_end = len(self.rows)
         self.proc.terminate()
+        try:                            # the sampler's own teardown (a driver client going away) must not overlap the NEXT timed region
+            self.proc.wait(timeout=3)
+        except Exception:
+            pass
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         rows = self.rows[mark:n_end] or self.rows[-1:]

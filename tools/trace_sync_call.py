@@ -5,7 +5,7 @@ import bench
 from veritasfi_b200 import _native as N, synth
 ctx = bench.Ctx(); ctx.rank, ctx.world, ctx.local_rank, ctx.dev = 0, 1, 0, torch.device("cuda", 0)
 torch.cuda.set_device(0)
-w = dict(bench.WORKLOADS["c3"])
+w = dict(bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "c3"])
 index, lo, hi = bench.build_dense_index(ctx, w["n"], w["d"], bench.SEED)
 index.set_option(N.OPT_PROFILE, 1)
 q = synth.dense_queries_torch(w["b"], w["d"], bench.SEED, ctx.dev)
