@@ -7,6 +7,10 @@
 // Workspace of its own taken from a pool (device scratch, prepared queries, certificate flag, events, a private stream
 // for host-buffer calls), so any number of threads may search one index at once; add/reserve/set_option take the writer
 // lock (not concurrent with search, as with faiss).
+//
+// Sharded search (vfi_index_search_begin_push, with api_exchange.h): the rescoring kernel of a batch is also the sender of
+// the multi-GPU exchange; the batch's certificate count reaches the host through mapped memory (no copy operation).
+// Debugging aids: VFI_TRACE_HOST (wall-clock phases of a host-buffer call), VFI_TRACE_STEPS (device time per stream operation).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>

@@ -1,8 +1,10 @@
 // dense_support.cuh — the bandwidth-bound kernels around the tensor-core pass:
 //   K6  prep_rows / prep_queries / normalize_l2   (cast, 3-term bf16 split, norms, epsilon)
 //   K1c cand_reduce                               (per-query union of the group buffers -> k' best)
-//   K2  canon_score + finalize                    (exact rescoring in the canonical order, final
-//                                                  (score desc, id asc) order, exactness certificate)
+//   tau_from_scores                               (admission hint: m-th largest sampled score, one warp per query)
+//   K2  rescore_finalize / canon_score + finalize (exact rescoring in the canonical order, final
+//                                                  (score desc, id asc) order, exactness certificate; rescore_finalize
+//                                                  also sends a sharded batch's rows to the peers, peer_exchange.cuh)
 //   K1b gemv_topk                                 (small query batches: pure HBM stream, no tensor cores)
 //
 // Canonical score (the parity contract, oracle/vfi_oracle.c:vfo_canon_dot): sequential fp64
